@@ -1,0 +1,184 @@
+/*
+ * lfi_b200.h — C ABI of the B200-native conditional-Glow hot path ("Let's Face It" MoGlow flow).
+ *
+ * The reference (jonepatr/lets_face_it) has no FFI layer: the path sits behind the Python module
+ * API of code/glow_pytorch/glow/{models,modules}.py.  These entry points are what a binding for
+ * that API binds (ctypes stub: lets_face_it_b200/_cabi.py).  Every function
+ *   - takes plain device pointers + sizes + a cudaStream_t (as void*), borrows them for the call,
+ *   - allocates nothing (the caller passes a workspace sized by the matching *_ws_bytes call),
+ *   - is stream-ordered, not thread-safe (the reference modules are stateful),
+ *   - returns 0 on success, a negative lfi_status otherwise; lfi_last_error() gives the text.
+ * All tensors are contiguous fp32 unless stated.  Row index of every "[M, ...]" matrix is
+ * m = t'*B + b (frame-major), t' = t - start_ts.
+ */
+#ifndef LFI_B200_H
+#define LFI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFI_ABI_VERSION 1
+#define LFI_NMOD 4 /* p1_face, p2_face, p1_speech, p2_speech — concat order of models.py:127-145 */
+
+typedef enum lfi_status {
+  LFI_OK = 0,
+  LFI_ERR_SHAPE = -1,   /* unsupported / inconsistent shape */
+  LFI_ERR_CUDA = -2,    /* a CUDA runtime call or launch failed */
+  LFI_ERR_ARG = -3,     /* null / misaligned pointer, bad flag */
+  LFI_ERR_WORKSPACE = -4 /* workspace too small */
+} lfi_status;
+
+/* GEMM numerics for the time-parallel contractions (cond_transform, gate-ih, encoders, wgrads). */
+typedef enum lfi_gemm_mode {
+  LFI_GEMM_FP32 = 0,       /* fp32 FFMA tiles (exact reference semantics)                       */
+  LFI_GEMM_BF16X3 = 1,     /* tcgen05 bf16 tiles, 3-product split (a_hi b_hi + a_hi b_lo + a_lo b_hi): fp32-grade */
+  LFI_GEMM_BF16 = 2        /* tcgen05 bf16 tiles, single product (throughput mode, looser bound) */
+} lfi_gemm_mode;
+
+/* Shapes of one model (final_model.yaml: C=56 K=16 H=128 D=512 G=3). */
+typedef struct lfi_shape {
+  int32_t C;              /* flow channels = Conditioning.p1_face.dim (models.py:473)            */
+  int32_t K;              /* flow steps K*L (models.py:417-436)                                   */
+  int32_t H;              /* coupling RNN hidden = Glow.hidden_channels, multiple of 4            */
+  int32_t D;              /* Conditioning.cond_dim                                                */
+  int32_t G;              /* gates: 3 = GRUCell (r,z,n), 4 = LSTMCell (i,f,g,o) (models.py:176-185) */
+  int32_t affine;         /* 1 = affine coupling, 0 = additive (models.py:331-341)                */
+  float scale_eps;        /* Glow.scale_eps: sigmoid(.+2).clamp(scale_eps)                        */
+  int32_t hist[LFI_NMOD]; /* history per modality, 0 = modality absent (never for p1_face)        */
+  int32_t dim[LFI_NMOD];  /* raw feature dim per modality                                         */
+  int32_t ehid[LFI_NMOD]; /* GRU encoder hidden ("enc: rnn"), 0 = "enc: none" (flattened window)  */
+  int32_t f_raw;          /* > 0: no FeatureEncoder, conditioning is a raw [B, f_raw] matrix (stand-alone
+                             FlowStep / FlowNet as in test_modules.py:30-67); hist/dim/ehid are ignored and only
+                             lfi_derive / lfi_flowstep are valid                                           */
+} lfi_shape;
+
+/* Trainable parameters, as [K, ...] blocks (flat storage, state-dict views live on top of it). */
+typedef struct lfi_params {
+  float *an_bias, *an_logs;          /* [K,C]      layers.k.actnorm.{bias,logs}  (modules.py:22-23)       */
+  float *w;                          /* [K,C,C]    composed 1x1 weight W (modules.py:163-173), z = x @ W   */
+  float *wc, *bc;                    /* [K,D,F],[K,D]  layers.k.f.cond_transform.0.{weight,bias}           */
+  float *w_ih, *b_ih;                /* [K,G*H,C/2+D],[K,G*H]  layers.k.f.rnn.{weight_ih,bias_ih}          */
+  float *w_hh, *b_hh;                /* [K,G*H,H],[K,G*H]      layers.k.f.rnn.{weight_hh,bias_hh}          */
+  float *wf, *bf, *lf;               /* [K,Co,H],[K,Co],[K,Co] layers.k.f.final_linear.{weight,bias,logs}  */
+  float *enc_w_ih[LFI_NMOD];         /* [3E,d]  feature_encoder.<m>_encoder.encoder.weight_ih_l0 (NULL if none) */
+  float *enc_w_hh[LFI_NMOD];         /* [3E,E]                                    weight_hh_l0             */
+  float *enc_b_ih[LFI_NMOD];         /* [3E]                                      bias_ih_l0               */
+  float *enc_b_hh[LFI_NMOD];         /* [3E]                                      bias_hh_l0               */
+} lfi_params;
+
+/* One batch: models.py:534-559 reads batch[m][:, t-h+1 : t+1]; tensors are [B, T, dim[m]] batch-first
+ * (mimicry_data_module.py layout).  mask[m] is NULL or the dropout mask [T', B, hist[m]] already
+ * scaled by 1/(1-p) (models.py:56-58). */
+typedef struct lfi_batch {
+  const float *x[LFI_NMOD];
+  const float *mask[LFI_NMOD];
+  int32_t B, T;
+} lfi_batch;
+
+const char *lfi_last_error(void);
+int lfi_abi_version(void);
+long lfi_launch_count(void); /* kernels launched by this library since load (bench.py gpu_launches) */
+
+/* ---- sizes ------------------------------------------------------------------------------- */
+int lfi_feature_dim(const lfi_shape *s);        /* F  = FeatureEncoder.dim (models.py:96-125)            */
+int lfi_feature_dim_folded(const lfi_shape *s); /* Fe = F with duplicated GRU halves folded (models.py:64) */
+int lfi_start_ts(const lfi_shape *s);           /* utils.py:44-50                                        */
+int lfi_coupling_out(const lfi_shape *s);       /* Co: f_seq output channels (models.py:276-298)         */
+size_t lfi_derived_bytes(const lfi_shape *s);
+size_t lfi_train_ws_bytes(const lfi_shape *s, int B, int T);
+size_t lfi_sample_ws_bytes(const lfi_shape *s, int B, int T, int chunk);
+size_t lfi_invconv_ws_bytes(int K, int C);
+size_t lfi_gemm_ws_bytes(void); /* scratch appended to every workspace for the tcgen05 operand staging */
+
+/* ---- derived weight cache (transposes, folded cond_transform, padded slices, W^-1) --------
+ * Must be re-run after every parameter update.  winv may be NULL (training only). */
+int lfi_derive(const lfi_shape *s, const lfi_params *p, const float *winv, void *derived, int gemm_mode,
+               void *stream);
+
+/* ---- 1x1 conv LU parametrisation (modules.py:149-178) ------------------------------------- */
+/* W = P (L*mask+I)(U*mask^T + diag(sign_s e^{log_s})) per step;  winv = U^-1 L^-1 P^-1 with the
+ * triangular inverses taken in fp64 and rounded to fp32 as the reference does (NULL = skip). */
+int lfi_invconv_compose(int K, int C, const float *p, const float *l, const float *u, const float *log_s,
+                        const float *sign_s, float *w, float *winv, void *ws, size_t ws_bytes, void *stream);
+/* chain rule of the composition: dl, du, dlog_s from dW (masked exactly as autograd masks them). */
+int lfi_invconv_compose_bwd(int K, int C, const float *p, const float *l, const float *u, const float *log_s,
+                            const float *sign_s, const float *dw, float *dl, float *du, float *dlog_s, void *ws,
+                            size_t ws_bytes, void *stream);
+
+/* ---- SeqGlow.forward (models.py:534-561): z, per-sample NLL, stash for backward ------------
+ * z [T',B,C]; nll [T',B] in bits WITHOUT the parameter-only constant  C*sum_k(sum logs_k + sum log_s_k)
+ * (modules.py:62,171), which the host adds (it owns log_s).  scale_out NULL or [K,B,C-C/2]: the
+ * last frame's coupling scale per step (FlowStep.scale under scale_logging, models.py:336-337). */
+int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params *p, const lfi_batch *b,
+                      float *z, float *nll, float *scale_out, void *ws, size_t ws_bytes, int gemm_mode,
+                      void *stream);
+/* Backward of the above given its output z and dnll [T',B] (dL/dnll); must follow the forward on
+ * the same workspace.  Gradients are ACCUMULATED into g (same layout as lfi_params; g->w receives
+ * dL/dW of the composed weight). */
+int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params *p, const lfi_batch *b,
+                      const float *z, const float *dnll, lfi_params *g, void *ws, size_t ws_bytes, int gemm_mode,
+                      void *stream);
+
+/* ---- SeqGlow.inference (models.py:567-596): persistent autoregressive sampler ---------------
+ * faces [B, seq_len, C] in/out: the first start_ts frames hold the seed (data["p1_face"]), frames
+ * t >= start_ts are written (prev_p1_faces of models.py:591; the reference returns [:, start_ts:]).
+ * Other modalities [B, T>=seq_len, d] (time stride b->T).  noise [T',B,C] (already scaled by eps)
+ * or NULL for zeros.  Frames are generated in chunks of `chunk`
+ * frames (static conditioning for a chunk is computed time-parallel, then one persistent kernel
+ * steps the chunk).  teacher_forced=1 implements SeqGlow.invert (models.py:617-645): noise is the
+ * given z sequence, conditioning uses batch.x[0] [B,T,C] ground truth; logdet_out [T',B] optional
+ * (coupling terms only, the host adds the parameter-only constant). */
+int lfi_seq_sample(const lfi_shape *s, const void *derived, const lfi_params *p, const lfi_batch *b,
+                   int seq_len, const float *noise, float *faces, float *logdet_out, int teacher_forced,
+                   int chunk, void *ws, size_t ws_bytes, int gemm_mode, void *stream);
+
+/* ---- FeatureEncoder.forward (models.py:127-145) for frames t0..t0+Tp-1: cond [Tp*B, Fe] (folded:
+ * each GRU-encoded modality contributes its final state once; the reference concatenates it twice). */
+size_t lfi_feature_ws_bytes(const lfi_shape *s, int B, int T, int Tp);
+int lfi_feature_encode(const lfi_shape *s, const lfi_params *p, const lfi_batch *b, int t0, int Tp, float *cond,
+                       void *ws, size_t ws_bytes, int gemm_mode, void *stream);
+
+/* ---- single-frame module API (FlowStep.forward models.py:305-373, test_modules.py) ----------
+ * One flow step k on one frame: x [B,C], cond [B,F] (raw, unfolded), h (and c) [B,H] in/out
+ * (NULL h_in = zeros, f_seq.init_rnn_hidden), logdet [B] in/out (coupling term only). */
+int lfi_flowstep(const lfi_shape *s, const void *derived, const lfi_params *p, int k, int reverse,
+                 const float *x, const float *cond, const float *h_in, const float *c_in, float *h_out,
+                 float *c_out, float *y, float *logdet, float *scale_out, int B, void *ws, size_t ws_bytes,
+                 void *stream);
+size_t lfi_flowstep_ws_bytes(const lfi_shape *s, int B);
+
+/* ---- primitives exposed for the module API and unit parity --------------------------------- */
+/* ActNorm2d.forward (modules.py:45-80) on [B,C]: reverse=0  y=(x+bias)*exp(logs); reverse=1 y=x*exp(-logs)-bias */
+int lfi_actnorm(const float *x, const float *bias, const float *logs, float *y, int B, int C, int reverse,
+                void *stream);
+/* C[M,N] = A[M,K] @ B[K,N] (+bias[N]) fp32 — InvertibleConv1x1.forward z = x @ W (modules.py:186) etc. */
+int lfi_matmul(const float *a, const float *b, const float *bias, float *c, int M, int N, int K, int transB,
+               void *stream);
+/* GaussianDiag.logp_simplified + SeqGlow.loss (modules.py:207-212, models.py:563-565):
+ * nll[b] = -(logdet[b] + sum_c -0.5 (z^2 + ln 2pi)) / ln 2 */
+int lfi_nll(const float *z, const float *logdet, float *nll, int B, int C, void *stream);
+
+/* fused gradient-norm clip + Adam over the flat parameter buffer (lets_face_it_glow.py:61-72,
+ * final_model.yaml:126,130): two launches, no host sync.  norm_scratch: 2 floats. */
+int lfi_clip_adam(float *theta, float *grad, float *m, float *v, size_t n, float lr, float beta1, float beta2,
+                  float eps, float max_norm, float grad_scale, int step, float *norm_scratch, void *stream);
+
+/* generic batched GEMM used by the time-parallel phases (exposed for unit parity of the tcgen05 path)
+ * C[b] = op(A[b]) op(B[b]) : transA: A stored [K,M]; transB: B stored [N,K]. epilogue flags below. */
+#define LFI_EPI_BIAS 1
+#define LFI_EPI_LRELU 2
+#define LFI_EPI_ACCUM 4
+#define LFI_EPI_LRELU_BWD 8
+int lfi_gemm(int mode, int transA, int transB, int M, int N, int K, const float *A, int lda, long strideA,
+             const float *B, int ldb, long strideB, float *C, int ldc, long strideC, const float *bias,
+             long strideBias, const float *aux, int ldaux, long strideAux, int batch, int epi, void *ws,
+             size_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFI_B200_H */

@@ -1,0 +1,369 @@
+// Small HBM-bound kernels around the GEMMs and the flow core: layout transforms of the derived weight
+// cache, window gathers, encoder GRU gate math, column sums, LU parametrisation helpers, clip + Adam.
+// All are coalesced, grid-stride where the size warrants it, warp-shuffle reduced.
+#include "aux_kernels.cuh"
+#include <cmath>
+
+namespace lfi {
+namespace aux {
+
+namespace {
+constexpr int TB = 256;
+inline int blocks_for(size_t n, int per = TB, int cap = 148 * 16) {
+  size_t b = (n + per - 1) / per;
+  if (b < 1) b = 1;
+  if (b > (size_t)cap) b = cap;
+  return (int)b;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+__global__ void gather2d_kernel(float *dst, int ld, const float *src, long sb, long si, long sj, int batch, int rows, int cols) {
+  const size_t n = (size_t)batch * rows * ld;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e % ld);
+    const size_t q = e / ld;
+    const int i = (int)(q % rows), b = (int)(q / rows);
+    dst[e] = j < cols ? src[(size_t)b * sb + (size_t)i * si + (size_t)j * sj] : 0.f;
+  }
+}
+int gather2d(float *dst, int ld, const float *src, long sb, long si, long sj, int batch, int rows, int cols, cudaStream_t st) {
+  gather2d_kernel<<<blocks_for((size_t)batch * rows * ld), TB, 0, st>>>(dst, ld, src, sb, si, sj, batch, rows, cols);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+struct FoldMap { int off[LFI_NMOD], offe[LFI_NMOD], we[LFI_NMOD], dup[LFI_NMOD]; int F, Fe; };
+static FoldMap make_fold(const Dims &d, const lfi_shape &s) {
+  FoldMap f;
+  for (int m = 0; m < LFI_NMOD; ++m) {
+    f.off[m] = d.enc_off[m]; f.offe[m] = d.enc_offe[m]; f.we[m] = d.enc_we[m];
+    f.dup[m] = (s.f_raw <= 0 && s.hist[m] > 0 && s.ehid[m] > 0) ? 1 : 0;
+  }
+  f.F = d.F; f.Fe = d.Fe;
+  return f;
+}
+__global__ void fold_wc_kernel(float *wcf, const float *wc, FoldMap f, size_t rows) {
+  const size_t n = rows * f.Fe;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e % f.Fe);
+    const size_t r = e / f.Fe;
+    int m = 0;
+#pragma unroll
+    for (int i = 1; i < LFI_NMOD; ++i) if (f.we[i] > 0 && j >= f.offe[i]) m = i;
+    const int jj = j - f.offe[m];
+    const float *src = wc + r * f.F + f.off[m] + jj;
+    wcf[e] = f.dup[m] ? src[0] + src[f.we[m]] : src[0];
+  }
+}
+int fold_wc(float *wcf, const float *wc, const Dims &d, const lfi_shape &s, cudaStream_t st) {
+  const size_t rows = (size_t)d.K * d.D;
+  fold_wc_kernel<<<blocks_for(rows * d.Fe), TB, 0, st>>>(wcf, wc, make_fold(d, s), rows);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+__global__ void unfold_wc_grad_kernel(float *dwc, const float *dwcf, FoldMap f, size_t rows) {
+  const size_t n = rows * f.Fe;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e % f.Fe);
+    const size_t r = e / f.Fe;
+    int m = 0;
+#pragma unroll
+    for (int i = 1; i < LFI_NMOD; ++i) if (f.we[i] > 0 && j >= f.offe[i]) m = i;
+    const int jj = j - f.offe[m];
+    float *dst = dwc + r * f.F + f.off[m] + jj;
+    const float g = dwcf[e];
+    dst[0] += g;
+    if (f.dup[m]) dst[f.we[m]] += g;
+  }
+}
+int unfold_wc_grad(float *dwc, const float *dwcf, const Dims &d, const lfi_shape &s, cudaStream_t st) {
+  const size_t rows = (size_t)d.K * d.D;
+  unfold_wc_grad_kernel<<<blocks_for(rows * d.Fe), TB, 0, st>>>(dwc, dwcf, make_fold(d, s), rows);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums: block = 32 columns x 8 row lanes, grid.y splits the rows; one atomic per column per block
+__global__ void colsum_kernel(float *out, const float *A, int ld, int rows, int cols, float scale, int rows_per_block) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  if (j < cols)
+    for (int r = r0 + ty; r < r1; r += 8) s += A[(size_t)r * ld + j];
+  part[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && j < cols) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s += part[i][tx];
+    atomicAdd(out + j, s * scale);
+  }
+}
+int colsum(float *out, const float *A, int ld, int rows, int cols, float scale, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return LFI_OK;
+  const int cb = (cols + 31) / 32;
+  int rb = (148 * 8 + cb - 1) / cb;
+  const int maxrb = (rows + 63) / 64;
+  if (rb > maxrb) rb = maxrb;
+  if (rb < 1) rb = 1;
+  const int rpb = (rows + rb - 1) / rb;
+  colsum_kernel<<<dim3(cb, rb), 256, 0, st>>>(out, A, ld, rows, cols, scale, rpb);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void actnorm_kernel(const float *x, const float *bias, const float *logs, float *y, size_t n, int C, int reverse) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    y[e] = reverse ? x[e] * expf(-logs[c]) - bias[c] : (x[e] + bias[c]) * expf(logs[c]);
+  }
+}
+int actnorm(const float *x, const float *bias, const float *logs, float *y, int B, int C, int reverse, cudaStream_t st) {
+  actnorm_kernel<<<blocks_for((size_t)B * C), TB, 0, st>>>(x, bias, logs, y, (size_t)B * C, C, reverse);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+__global__ void nll_kernel(const float *z, const float *logdet, float *out, int B, int C) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) { const float v = z[(size_t)b * C + c]; s += v * v; }
+  s = warp_sum(s);
+  if (lane == 0) out[b] = -(logdet[b] - 0.5f * (s + (float)C * kLog2Pi)) / kLn2;
+}
+int nll(const float *z, const float *logdet, float *out, int B, int C, cudaStream_t st) {
+  nll_kernel<<<(B + 7) / 8, 256, 0, st>>>(z, logdet, out, B, C);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void gather_windows_kernel(float *dst, int ld, int layout_steps, const float *x, const float *mask, int B, int T,
+                                      int dim, int hist, int off, int t0, int Tp) {
+  const size_t M = (size_t)Tp * B;
+  const size_t n = M * hist * dim;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % dim);
+    size_t q = e / dim;
+    int s; size_t m;
+    if (layout_steps) { m = q % M; s = (int)(q / M); }
+    else { s = (int)(q % hist); m = q / hist; }
+    const int b = (int)(m % B), tp = (int)(m / B);
+    const int tau = t0 + tp - hist + off + s;
+    float v = x[((size_t)b * T + tau) * dim + c];
+    if (mask) v *= mask[m * hist + s];
+    if (layout_steps) dst[((size_t)s * M + m) * ld + c] = v;
+    else dst[m * ld + (size_t)s * dim + c] = v;
+  }
+}
+int gather_windows(float *dst, int ld, int layout_steps, const float *x, const float *mask, int B, int T, int dim, int hist,
+                   int off, int t0, int Tp, cudaStream_t st) {
+  gather_windows_kernel<<<blocks_for((size_t)Tp * B * hist * dim), TB, 0, st>>>(dst, ld, layout_steps, x, mask, B, T, dim,
+                                                                                hist, off, t0, Tp);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void enc_gate_fwd_kernel(EncStep a) {
+  const size_t M = (size_t)a.Tp * a.B;
+  const int E = a.E;
+  const size_t n = M * E;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(idx % E);
+    const size_t m = idx / E;
+    const int b = (int)(m % a.B), tp = (int)(m / a.B);
+    const int tau = a.t0 + tp - a.hist + 1 + a.s;
+    const float mk = a.mask ? a.mask[m * a.hist + a.s] : 1.0f;
+    const float *xp = a.xp + ((size_t)b * a.T + tau) * 3 * E;
+    const float air = mk * xp[e] + a.b_ih[e], aiu = mk * xp[E + e] + a.b_ih[E + e], ain = mk * xp[2 * E + e] + a.b_ih[2 * E + e];
+    float ahr = a.b_hh[e], ahu = a.b_hh[E + e], ahn = a.b_hh[2 * E + e];
+    float hp = 0.f;
+    if (a.gh) {
+      const float *g = a.gh + m * 3 * E;
+      ahr += g[e]; ahu += g[E + e]; ahn += g[2 * E + e];
+    }
+    if (a.hprev) hp = a.hprev[idx];
+    const float rg = sigmoidf_(air + ahr), ug = sigmoidf_(aiu + ahu);
+    const float ng = tanhf(ain + rg * ahn);
+    const float h = ng + ug * (hp - ng);
+    a.h[idx] = h;
+    if (a.gates) { float *g = a.gates + m * 3 * E; g[e] = rg; g[E + e] = ug; g[2 * E + e] = ng; }
+    if (a.ahn) a.ahn[idx] = ahn;
+    if (a.cond) a.cond[m * a.cond_ld + e] = h;
+  }
+}
+int enc_gate_fwd(const EncStep &a, cudaStream_t st) {
+  enc_gate_fwd_kernel<<<blocks_for((size_t)a.Tp * a.B * a.E), TB, 0, st>>>(a);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+__global__ void enc_gate_bwd_kernel(EncStepBwd a) {
+  const int E = a.E;
+  const size_t n = (size_t)a.M * E;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(idx % E);
+    const size_t m = idx / E;
+    float dh = a.dh[idx];
+    if (a.dh_extra) dh += a.dh_extra[m * a.dh_extra_ld + e];
+    const float *g = a.gates + m * 3 * E;
+    const float rg = g[e], ug = g[E + e], ng = g[2 * E + e];
+    const float hp = a.hprev ? a.hprev[idx] : 0.f;
+    const float an = a.ahn[idx];
+    const float dn = dh * (1.0f - ug), du = dh * (hp - ng);
+    const float dan = dn * (1.0f - ng * ng), dau = du * ug * (1.0f - ug), dar = dan * an * rg * (1.0f - rg);
+    float *di = a.dai + m * 3 * E, *dhh = a.dah + m * 3 * E;
+    di[e] = dar; di[E + e] = dau; di[2 * E + e] = dan;
+    dhh[e] = dar; dhh[E + e] = dau; dhh[2 * E + e] = dan * rg;
+    a.dh[idx] = dh * ug;
+  }
+}
+int enc_gate_bwd(const EncStepBwd &a, cudaStream_t st) {
+  enc_gate_bwd_kernel<<<blocks_for((size_t)a.M * a.E), TB, 0, st>>>(a);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void lu_build_kernel(float *Lm, float *Um, const float *l, const float *u, const float *log_s, const float *sign_s, int K, int C) {
+  const size_t n = (size_t)K * C * C;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e % C), i = (int)((e / C) % C), k = (int)(e / ((size_t)C * C));
+    Lm[e] = i > j ? l[e] : (i == j ? 1.0f : 0.0f);
+    Um[e] = i < j ? u[e] : (i == j ? sign_s[k * C + i] * expf(log_s[k * C + i]) : 0.0f);
+  }
+}
+int lu_build(float *Lm, float *Um, const float *l, const float *u, const float *log_s, const float *sign_s, int K, int C, cudaStream_t st) {
+  lu_build_kernel<<<blocks_for((size_t)K * C * C), TB, 0, st>>>(Lm, Um, l, u, log_s, sign_s, K, C);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+// Triangular inverses in fp64 (the reference inverts L and U with torch.inverse(x.double()).float(),
+// modules.py:175-176).  Thread j solves column j by substitution; scratch holds the fp64 columns.
+__global__ void tri_inverse_kernel(float *Linv, float *Uinv, double *scratch, const float *Lm, const float *Um, int C) {
+  const int k = blockIdx.x, which = blockIdx.y, j = threadIdx.x;
+  if (j >= C) return;
+  const float *A = (which == 0 ? Lm : Um) + (size_t)k * C * C;
+  float *out = (which == 0 ? Linv : Uinv) + (size_t)k * C * C;
+  double *x = scratch + ((size_t)(k * 2 + which)) * C * C;  // x[i*C + j]
+  if (which == 0) {
+    for (int i = 0; i < C; ++i) {
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int m = 0; m < i; ++m) s -= (double)A[i * C + m] * x[m * C + j];
+      x[i * C + j] = s / (double)A[i * C + i];
+    }
+  } else {
+    for (int i = C - 1; i >= 0; --i) {
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int m = i + 1; m < C; ++m) s -= (double)A[i * C + m] * x[m * C + j];
+      x[i * C + j] = s / (double)A[i * C + i];
+    }
+  }
+  for (int i = 0; i < C; ++i) out[i * C + j] = (float)x[i * C + j];
+}
+int tri_inverse_f64(float *Linv, float *Uinv, double *scratch, const float *Lm, const float *Um, int K, int C, cudaStream_t st) {
+  tri_inverse_kernel<<<dim3(K, 2), round_up(C, 32), 0, st>>>(Linv, Uinv, scratch, Lm, Um, C);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+__global__ void lu_mask_grads_kernel(float *dl, float *du, float *dlog_s, const float *dL, const float *dU, const float *log_s,
+                                     const float *sign_s, int K, int C) {
+  const size_t n = (size_t)K * C * C;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(e % C), i = (int)((e / C) % C), k = (int)(e / ((size_t)C * C));
+    if (i > j) dl[e] += dL[e];
+    if (i < j) du[e] += dU[e];
+    if (i == j) dlog_s[k * C + i] += dU[e] * sign_s[k * C + i] * expf(log_s[k * C + i]);
+  }
+}
+int lu_mask_grads(float *dl, float *du, float *dlog_s, const float *dL, const float *dU, const float *log_s, const float *sign_s,
+                  int K, int C, cudaStream_t st) {
+  lu_mask_grads_kernel<<<blocks_for((size_t)K * C * C), TB, 0, st>>>(dl, du, dlog_s, dL, dU, log_s, sign_s, K, C);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void sumsq_kernel(float *out, const float *g, size_t n) {
+  __shared__ float part[TB / 32];
+  float s = 0.f;
+  const size_t n4 = n / 4;
+  const float4 *g4 = reinterpret_cast<const float4 *>(g);
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = g4[e];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (size_t e = n4 * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) s += g[e] * g[e];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < TB / 32 ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+int sumsq(float *out2, const float *g, size_t n, cudaStream_t st) {
+  LFI_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(float), st));
+  sumsq_kernel<<<blocks_for(n / 4 + 1, TB, 148 * 4), TB, 0, st>>>(out2, g, n);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+// torch.nn.utils.clip_grad_norm_ (coef = max_norm / (norm + 1e-6), clamped to 1) followed by torch.optim.Adam
+// (no weight decay, no amsgrad): the reference's configure_optimizers + gradient_clip_val.
+__global__ void clip_adam_kernel(float *theta, const float *grad, float *m, float *v, size_t n, float lr, float b1, float b2,
+                                 float omb1, float omb2, float eps, float max_norm, float grad_scale, float bc1,
+                                 float bc2_sqrt, const float *sumsq_in) {
+  const float norm = sqrtf(sumsq_in[0]) * grad_scale;
+  float coef = 1.0f;
+  if (max_norm > 0.f) coef = fminf(max_norm / (norm + 1e-6f), 1.0f);
+  const float gs = grad_scale * coef;
+  const float step = lr / bc1;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const float g = grad[e] * gs;
+    const float mm = b1 * m[e] + omb1 * g;
+    const float vv = b2 * v[e] + omb2 * g * g;
+    m[e] = mm; v[e] = vv;
+    theta[e] -= step * mm / (sqrtf(vv) / bc2_sqrt + eps);
+  }
+}
+int clip_adam(float *theta, const float *grad, float *m, float *v, size_t n, float lr, float b1, float b2, float eps,
+              float max_norm, float grad_scale, int step, const float *sumsq_in, cudaStream_t st) {
+  // scalar coefficients in double, as torch.optim.Adam computes them on the host
+  const double b1d = (double)b1, b2d = (double)b2;
+  const float bc1 = (float)(1.0 - pow(b1d, (double)step));
+  const float bc2s = (float)sqrt(1.0 - pow(b2d, (double)step));
+  clip_adam_kernel<<<blocks_for(n, TB, 148 * 8), TB, 0, st>>>(theta, grad, m, v, n, lr, b1, b2, (float)(1.0 - b1d),
+                                                               (float)(1.0 - b2d), eps, max_norm, grad_scale, bc1, bc2s,
+                                                               sumsq_in);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+__global__ void fill_kernel(float *p, float v, size_t n) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) p[e] = v;
+}
+int fill(float *p, float v, size_t n, cudaStream_t st) {
+  if (n == 0) return LFI_OK;
+  fill_kernel<<<blocks_for(n), TB, 0, st>>>(p, v, n);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+}  // namespace aux
+}  // namespace lfi

@@ -1,0 +1,82 @@
+// Kernel argument blocks and host launchers of the sequential flow core.
+#pragma once
+#include "core_tile.cuh"
+
+namespace lfi {
+namespace core {
+
+// Activation stash written by the forward wavefront and consumed by the backward one.
+// Every array is [K][Tp][B][width] (cell-major), fp32.
+struct Stash {
+  float *y;      // [.,C]   ActNorm output (input of the 1x1 conv)
+  float *zf;     // [.,C]   1x1 conv output (z1 | z2)
+  float *h;      // [.,H]   RNN state after the cell
+  float *c;      // [.,H]   LSTM cell state after the cell (G == 4)
+  float *gates;  // [.,GH]  post-activation gates
+  float *ahn;    // [.,H]   GRU: h-side pre-activation of the n gate
+  float *o;      // [.,Co]  LinearZeros output
+  float *xin;    // [.,C]   input of step k (k >= 1; slot k = K unused)
+};
+
+struct FwdArgs {
+  Dims d;
+  DerivedView dv;
+  int B, Tp;
+  int k_first, k_last;        // step range evaluated (module API: a single step)
+  const float *x0;            // input of step k_first: element (b, t, c) at x0[b*x_sb + t*x_st + c]
+  long x_sb, x_st;
+  const float *G;             // [Tp*B][g_ld] gate-ih pre-activations incl. b_ih; columns (k - g_k0)*GH ...
+  long g_ld; int g_k0;
+  const float *h0, *c0;       // [K][B][H] or nullptr (zeros)
+  float *xin;                 // handoff between steps
+  float *st_y, *st_zf, *st_h, *st_c, *st_gates, *st_ahn, *st_o;
+  float *ld;                  // [Tp][B] running log-det (coupling terms only)
+  int ld_accumulate;          // 1: ld already holds the caller's log-det
+  float *nll;                 // [Tp][B] or nullptr
+  float *z_out;               // [Tp][B][C] output of step k_last
+  float *scale_out;           // [K][B][Cz] or nullptr (FlowStep.scale, models.py:336-337)
+};
+
+struct InvArgs {
+  Dims d;
+  DerivedView dv;
+  int B, Tc;                  // frames in this launch
+  int k_hi, k_lo;             // steps evaluated per frame, k_hi down to k_lo (whole flow: K-1 .. 0)
+  int g_k0;                   // step whose gate-ih pre-activations sit at column 0 of G
+  int t_abs0;                 // absolute frame index (into faces) of the first generated frame
+  int t_rel0;                 // index of that frame relative to start_ts (into noise / logdet_out)
+  const float *noise;         // [T'][B][C] or nullptr (zeros)
+  const float *G; long g_ld;  // teacher-forced: [Tc*B][K*GH] gate-ih pre-activations (chunk-relative rows)
+  const float *cstatic; long cs_ld;  // AR: [Tc*B][K*D] static part of cond_transform pre-activation (incl. bias)
+  const float *faces; long f_sb, f_st;        // AR window source (seed + generated frames)
+  float *faces_out; long fo_sb, fo_st;        // where frame t_abs is written
+  float *hstate, *cstate;     // [K][B][H] carried RNN state (in/out)
+  float *logdet_out;          // [T'][B] or nullptr (coupling terms only)
+};
+
+struct BwdArgs {
+  Dims d;
+  DerivedView dv;
+  int B, Tp;
+  const float *dnll;          // [Tp][B] dL/dnll
+  const float *z;             // [Tp][B][C] forward output (for d nll / d z)
+  Stash st;
+  float *dx;                  // [K][Tp][B][C]  grad wrt input of step k (handoff)
+  float *dh;                  // [K][Tp][B][H]  grad wrt h[k][t-1] produced by cell (k,t)
+  float *dc;                  // [K][Tp][B][H]  LSTM
+  float *dG;                  // [Tp*B][K*GH]   dA_i (grad wrt gate-ih pre-activation)
+  float *dAh;                 // [K][Tp][B][GH] dA_h (for dW_hh)
+  float *dO;                  // [K][Tp][B][Co] grad wrt the LinearZeros matmul output (dO * exp(3 logs)), for dWf
+  float *dzf;                 // [K][Tp][B][C]  grad wrt 1x1 conv output (for dW)
+  // small per-channel gradients accumulated with atomics, [K][.]
+  float *g_an_bias, *g_an_logs, *g_b_hh, *g_bf, *g_lf;
+};
+
+int fwd_smem_bytes(const Dims &d, int R);
+int choose_rpt(const Dims &d, int B, bool bwd, bool sampler);
+int launch_fwd(const FwdArgs &a, cudaStream_t st);
+int launch_inv(const InvArgs &a, cudaStream_t st);
+int launch_bwd(const BwdArgs &a, cudaStream_t st);
+
+}  // namespace core
+}  // namespace lfi

@@ -1,0 +1,237 @@
+// Sequential flow core, backward direction: reverse wavefronts over the (step k, frame t) cells.
+// Cell (k,t) consumes d(output of step k) from cell (k+1,t) and d(h[k][t]) from cell (k,t+1) (BPTT of the
+// coupling RNN, models.py:193-214) and produces d(input of step k), d(h[k][t-1]), the gate gradients dA_i /
+// dA_h (whose weight gradients are taken afterwards as time-parallel GEMMs over the stash) and the small
+// per-channel gradients (ActNorm bias/logs, b_hh, LinearZeros bias/logs) by per-CTA column sums + atomics.
+#include "core_api.cuh"
+
+namespace lfi {
+namespace core {
+
+template <int RPT>
+__global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmin) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int R = Tile<RPT>::R, RS = Tile<RPT>::RS;
+  const Dims &d = a.d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = kmin + blockIdx.y, t = wave - k;
+  const int row0 = blockIdx.x * R, nrows = min(R, a.B - row0);
+  const int C = d.C, Ci = d.Ci, Cz = d.Cz, Co = d.Co, H = d.H, GH = d.GH, B = a.B, Tp = a.Tp;
+  const bool gru = d.G == 3;
+  const SmemPlan sp = plan_smem(d, R, true, false);
+  const StepWeights w = a.dv.step(d, k);
+  const size_t cell = (size_t)k * Tp + t;
+  const int pC = odd(C), pO = odd(Co > C ? Co : C), pS = odd(GH), pH = odd(H);
+  float *xs = sm + sp.xs, *zact = sm + sp.zact, *zrow = sm + sp.zrow, *hp = sm + sp.hp, *cp = sm + sp.cp;
+  float *S = sm + sp.S, *ahn = sm + sp.ahn, *orow = sm + sp.orow, *dact = sm + sp.dact, *dxr = sm + sp.dxr;
+  float *dhr = sm + sp.dhr, *prod = sm + sp.prod, *cn = sm + sp.cn, *dldr = sm + sp.ldacc;
+
+  // ---- A. loads ---------------------------------------------------------------------------------
+  for (int e = tid; e < R * C; e += NT) {
+    const int r = e / C, c = e - r * C;
+    float dxo = 0.f, zf = 0.f;
+    if (r < nrows) {
+      const int b = row0 + r;
+      zf = a.st.zf[(cell * B + b) * C + c];
+      if (k == d.K - 1) dxo = a.dnll[(size_t)t * B + b] * a.z[((size_t)t * B + b) * C + c] / kLn2;  // d nll / d z = z / ln2
+      else dxo = a.dx[((cell + Tp) * B + b) * C + c];
+    }
+    dxr[r * pC + c] = dxo;
+    zrow[r * pC + c] = zf;
+  }
+  for (int e = tid; e < R * Co; e += NT) {
+    const int r = e / Co, j = e - r * Co;
+    orow[r * pO + j] = (r < nrows) ? a.st.o[(cell * B + row0 + r) * Co + j] : 0.f;
+  }
+  if (tid < R) dldr[tid] = (tid < nrows) ? -a.dnll[(size_t)t * B + row0 + tid] / kLn2 : 0.f;  // d nll / d logdet
+  for (int e = tid; e < R * GH; e += NT) {
+    const int r = e / GH, j = e - r * GH;
+    S[r * pS + j] = (r < nrows) ? a.st.gates[(cell * B + row0 + r) * GH + j] : 0.f;
+  }
+  for (int e = tid; e < R * H; e += NT) {
+    const int r = e / H, m = e - r * H;
+    float hv = 0.f, cv = 0.f, cnv = 0.f, an = 0.f;
+    if (r < nrows) {
+      const size_t idx = (cell * B + row0 + r) * H + m;
+      if (t > 0) {
+        hv = a.st.h[idx - (size_t)B * H];
+        if (!gru) cv = a.st.c[idx - (size_t)B * H];
+      }
+      if (gru) {
+        an = a.st.ahn[idx];
+      } else {
+        cnv = a.st.c[idx];
+        an = (t < Tp - 1) ? a.dc[idx + (size_t)B * H] : 0.f;  // dc flowing back from cell (k, t+1)
+      }
+    }
+    hp[m * RS + r] = hv;
+    ahn[r * pH + m] = an;
+    if (!gru) { cp[m * RS + r] = cv; cn[m * RS + r] = cnv; }
+  }
+  __syncthreads();
+
+  // ---- B. coupling backward (models.py:331-341) ---------------------------------------------------
+  for (int r = warp; r < R; r += NT / 32) {
+    const float dld = dldr[r];
+    for (int q = lane; q < Cz; q += 32) {
+      const float dz2n = dxr[r * pC + Ci + q];
+      if (d.affine) {
+        const float shift = orow[r * pO + 2 * q], sc = orow[r * pO + 2 * q + 1];
+        const float sg = sigmoidf_(sc + 2.0f), s = fmaxf(sg, d.eps);
+        const float z2 = zrow[r * pC + Ci + q];
+        const float ds = dz2n * (z2 + shift) + dld / s;
+        const float dz2 = dz2n * s;
+        const float dsc = (sg >= d.eps) ? ds * sg * (1.0f - sg) : 0.f;
+        prod[r * pO + 2 * q] = dz2 * shift;
+        prod[r * pO + 2 * q + 1] = dsc * sc;
+        orow[r * pO + 2 * q] = dz2;
+        orow[r * pO + 2 * q + 1] = dsc;
+        xs[(2 * q) * RS + r] = dz2 * expf(3.0f * w.lf[2 * q]);
+        xs[(2 * q + 1) * RS + r] = dsc * expf(3.0f * w.lf[2 * q + 1]);
+        zrow[r * pC + Ci + q] = dz2;
+      } else {
+        prod[r * pO + q] = dz2n * orow[r * pO + q];
+        orow[r * pO + q] = dz2n;
+        xs[q * RS + r] = dz2n * expf(3.0f * w.lf[q]);
+        zrow[r * pC + Ci + q] = dz2n;
+      }
+    }
+    for (int c = lane; c < Ci; c += 32) zrow[r * pC + c] = dxr[r * pC + c];
+  }
+  __syncthreads();
+  // dlin stash (= dO * e3, for dWf) + LinearZeros bias/logs gradients
+  // (o = (lin + bf) * e3  =>  d bf = e3 * sum dO, d lf = 3 * sum dO*o)
+  for (int e = tid; e < nrows * Co; e += NT) {
+    const int r = e / Co, j = e - r * Co;
+    a.dO[(cell * B + row0 + r) * Co + j] = xs[j * RS + r];
+  }
+  for (int j = tid; j < Co; j += NT) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < nrows; ++r) { s1 += orow[r * pO + j]; s2 += prod[r * pO + j]; }
+    atomicAdd(&a.g_bf[(size_t)k * Co + j], s1 * expf(3.0f * w.lf[j]));
+    atomicAdd(&a.g_lf[(size_t)k * Co + j], 3.0f * s2);
+  }
+
+  // ---- E. dh = dlin @ Wf (+ dh from the next frame) ------------------------------------------------
+  tile_gemm<RPT>(xs, w.Wf, H, Co, H, sm + sp.wst, [&](int r, int j, float v) {
+    if (r < nrows && t < Tp - 1) v += a.dh[((cell + 1) * B + row0 + r) * H + j];
+    dhr[r * pH + j] = v;
+  });
+  __syncthreads();
+
+  // ---- G. gate backward ------------------------------------------------------------------------------
+  for (int e = tid; e < R * H; e += NT) {
+    const int r = e % R, m = e / R;
+    float *s = S + r * pS;
+    const float dh = dhr[r * pH + m];
+    if (gru) {
+      const float rg = s[m], ug = s[H + m], ng = s[2 * H + m], hpv = hp[m * RS + r], an = ahn[r * pH + m];
+      const float dn = dh * (1.0f - ug), du = dh * (hpv - ng);
+      const float dan = dn * (1.0f - ng * ng), dau = du * ug * (1.0f - ug), dar = dan * an * rg * (1.0f - rg);
+      s[m] = dar; s[H + m] = dau; s[2 * H + m] = dan;
+      ahn[r * pH + m] = dan * rg;
+      dact[m * RS + r] = dar; dact[(H + m) * RS + r] = dau; dact[(2 * H + m) * RS + r] = dan;
+      dact[(GH + m) * RS + r] = dan * rg;
+      dhr[r * pH + m] = dh * ug;
+    } else {
+      const float ig = s[m], fg = s[H + m], gg = s[2 * H + m], og = s[3 * H + m];
+      const float tc = tanhf(cn[m * RS + r]);
+      const float dc = dh * og * (1.0f - tc * tc) + ahn[r * pH + m];
+      const float dai = dc * gg * ig * (1.0f - ig), daf = dc * cp[m * RS + r] * fg * (1.0f - fg);
+      const float dag = dc * ig * (1.0f - gg * gg), dao = dh * tc * og * (1.0f - og);
+      s[m] = dai; s[H + m] = daf; s[2 * H + m] = dag; s[3 * H + m] = dao;
+      dact[m * RS + r] = dai; dact[(H + m) * RS + r] = daf; dact[(2 * H + m) * RS + r] = dag;
+      dact[(3 * H + m) * RS + r] = dao;
+      ahn[r * pH + m] = dc * fg;
+      dhr[r * pH + m] = 0.f;
+    }
+  }
+  __syncthreads();
+  // dA_i -> dG (time-parallel backward + db_ih), dA_h stash (dW_hh), db_hh, LSTM dc_prev
+  for (int e = tid; e < nrows * GH; e += NT) {
+    const int r = e / GH, j = e - r * GH;
+    const float vi = S[r * pS + j];
+    const float vh = (gru && j >= 2 * H) ? ahn[r * pH + j - 2 * H] : vi;
+    a.dG[((size_t)t * B + row0 + r) * ((size_t)d.K * GH) + (size_t)k * GH + j] = vi;
+    a.dAh[(cell * B + row0 + r) * GH + j] = vh;
+  }
+  for (int j = tid; j < GH; j += NT) {
+    float s1 = 0.f;
+    if (gru && j >= 2 * H) {
+      for (int r = 0; r < nrows; ++r) s1 += ahn[r * pH + j - 2 * H];
+    } else {
+      for (int r = 0; r < nrows; ++r) s1 += S[r * pS + j];
+    }
+    atomicAdd(&a.g_b_hh[(size_t)k * GH + j], s1);
+  }
+  if (!gru && t > 0)
+    for (int e = tid; e < nrows * H; e += NT) {
+      const int r = e / H, j = e - r * H;
+      a.dc[(cell * B + row0 + r) * H + j] = ahn[r * pH + j];
+    }
+
+  // ---- I. dh_prev += dA_h @ W_hh ;  J. dz1 += dA_i @ W_ih[:, :Ci] ----------------------------------
+  tile_gemm<RPT>(dact, w.Whh, H, GH, H, sm + sp.wst, [&](int r, int j, float v) { dhr[r * pH + j] += v; },
+                 gru ? 2 * H : (1 << 30), gru ? H : 0, 0);
+  tile_gemm<RPT>(dact, w.WihZ, d.Cip, GH, Ci, sm + sp.wst, [&](int r, int j, float v) { zrow[r * pC + j] += v; });
+  __syncthreads();
+  if (t > 0)
+    for (int e = tid; e < nrows * H; e += NT) {
+      const int r = e / H, j = e - r * H;
+      a.dh[(cell * B + row0 + r) * H + j] = dhr[r * pH + j];
+    }
+  for (int e = tid; e < R * C; e += NT) {
+    const int r = e / C, c = e - r * C;
+    const float v = zrow[r * pC + c];
+    zact[c * RS + r] = v;
+    if (r < nrows) a.dzf[(cell * B + row0 + r) * C + c] = v;
+  }
+
+  // ---- K. dy = dzf @ W^T ; ActNorm backward (modules.py:45-66) --------------------------------------
+  tile_gemm<RPT>(zact, w.WT, d.Cp, C, C, sm + sp.wst, [&](int r, int j, float dy) {
+    const float y = (r < nrows) ? a.st.y[(cell * B + row0 + r) * C + j] : 0.f;
+    dxr[r * pC + j] = dy * expf(w.an_logs[j]);
+    prod[r * pO + j] = dy * y;
+  });
+  __syncthreads();
+  if (k > 0)
+    for (int e = tid; e < nrows * C; e += NT) {
+      const int r = e / C, c = e - r * C;
+      a.dx[(cell * B + row0 + r) * C + c] = dxr[r * pC + c];
+    }
+  for (int c = tid; c < C; c += NT) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < nrows; ++r) { s1 += dxr[r * pC + c]; s2 += prod[r * pO + c]; }
+    atomicAdd(&a.g_an_bias[(size_t)k * C + c], s1);
+    atomicAdd(&a.g_an_logs[(size_t)k * C + c], s2);
+  }
+}
+
+template <int RPT> static int launch_bwd_t(const BwdArgs &a, cudaStream_t st) {
+  constexpr int R = Tile<RPT>::R;
+  const int bytes = plan_smem(a.d, R, true, false).total * (int)sizeof(float);
+  LFI_CUDA(cudaFuncSetAttribute(core_bwd_wave<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  const int tiles = (a.B + R - 1) / R, K = a.d.K;
+  for (int wave = a.Tp + K - 2; wave >= 0; --wave) {
+    const int k0 = max(0, wave - a.Tp + 1), k1 = min(K - 1, wave);
+    dim3 grid(tiles, k1 - k0 + 1);
+    core_bwd_wave<RPT><<<grid, NT, bytes, st>>>(a, wave, k0);
+  }
+  LFI_LAUNCH_CHECK_N(a.Tp + K - 1);
+  return LFI_OK;
+}
+
+int launch_bwd(const BwdArgs &a, cudaStream_t st) {
+  const int rpt = choose_rpt(a.d, a.B, true, false);
+  switch (rpt) {
+    case 8: return launch_bwd_t<8>(a, st);
+    case 4: return launch_bwd_t<4>(a, st);
+    case 2: return launch_bwd_t<2>(a, st);
+    case 1: return launch_bwd_t<1>(a, st);
+  }
+  set_error("flow core backward: shape does not fit shared memory (H=%d G=%d C=%d)", a.d.H, a.d.G, a.d.C);
+  return LFI_ERR_SHAPE;
+}
+
+}  // namespace core
+}  // namespace lfi

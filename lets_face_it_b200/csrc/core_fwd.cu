@@ -1,0 +1,369 @@
+// Sequential flow core, forward direction (training / eval) and inverse direction (sampling / invert).
+//
+//   forward : FlowStep.normal_flow  (models.py:311-342) for every (step k, frame t) cell, scheduled as
+//             anti-diagonal wavefronts: cells with k + t = const are independent (cell (k,t) needs the
+//             output of (k-1,t) and the RNN state of (k,t-1)), so one launch evaluates up to K cells for
+//             all sequence tiles at once.  Weights stream from L2 once per CTA per launch.
+//   inverse : FlowStep.reverse_flow (models.py:345-373); strictly serial in (t, k) for a sequence, so one
+//             persistent CTA per sequence tile walks all frames and steps with no host round-trip
+//             (SeqGlow.inference models.py:581-594 / SeqGlow.invert 617-645).
+#include "core_tile.cuh"
+#include "core_api.cuh"
+#include <cstdlib>
+
+namespace lfi {
+namespace core {
+
+// ------------------------------------------------------------------------------------------------
+// coupling network f_seq (models.py:204-214): S <- gate pre-activations, h (c) update, o = LinearZeros(h)
+// in : sm[zact] rows [0,Ci) = z1 (act layout), sm[hp] = h_prev, sm[cp] = c_prev (LSTM)
+//      Grow != nullptr: S = G[row] (+ z1 part + h part);  else S already holds b_ih + c @ W_ih[:, Ci:]^T
+// out: sm[hp] = h_new, sm[cp] = c_new, sm[orow] = o; optional stashes
+template <int RPT>
+__device__ __forceinline__ void coupling_net(const Dims &d, const StepWeights &w, const SmemPlan &sp, float *sm,
+                                             int nrows, const float *Grow, long g_ld, float *st_gates, float *st_ahn,
+                                             float *st_h, float *st_c, float *st_o) {
+  constexpr int R = Tile<RPT>::R, RS = Tile<RPT>::RS;
+  const int tid = threadIdx.x;
+  const int H = d.H, GH = d.GH, pS = odd(GH), pH = odd(H), pO = odd(d.Co > d.C ? d.Co : d.C);
+  float *S = sm + sp.S, *ahn = sm + sp.ahn, *hp = sm + sp.hp, *cp = sm + sp.cp, *orow = sm + sp.orow;
+
+  // z1 part (and G init)
+  tile_gemm<RPT>(sm + sp.zact, w.WzT, GH, d.Ci, GH, sm + sp.wst, [&](int r, int j, float v) {
+    if (Grow) S[r * pS + j] = v + (r < nrows ? Grow[(size_t)r * g_ld + j] : 0.f);
+    else S[r * pS + j] += v;
+  });
+  // h part
+  const bool gru = d.G == 3;
+  tile_gemm<RPT>(hp, w.WhhT, GH, H, GH, sm + sp.wst, [&](int r, int j, float v) {
+    v += w.b_hh[j];
+    if (gru && j >= 2 * H) ahn[r * pH + (j - 2 * H)] = v;
+    else S[r * pS + j] += v;
+  });
+  __syncthreads();
+  // gate math: lanes along rows
+  for (int e = tid; e < R * H; e += NT) {
+    const int r = e % R, m = e / R;
+    float *s = S + r * pS;
+    if (gru) {
+      const float rg = sigmoidf_(s[m]), ug = sigmoidf_(s[H + m]);
+      const float ng = tanhf(s[2 * H + m] + rg * ahn[r * pH + m]);
+      const float hprev = hp[m * RS + r];
+      s[m] = rg; s[H + m] = ug; s[2 * H + m] = ng;
+      hp[m * RS + r] = ng + ug * (hprev - ng);
+    } else {
+      const float ig = sigmoidf_(s[m]), fg = sigmoidf_(s[H + m]), gg = tanhf(s[2 * H + m]), og = sigmoidf_(s[3 * H + m]);
+      const float cn = fg * cp[m * RS + r] + ig * gg;
+      s[m] = ig; s[H + m] = fg; s[2 * H + m] = gg; s[3 * H + m] = og;
+      cp[m * RS + r] = cn;
+      hp[m * RS + r] = og * tanhf(cn);
+    }
+  }
+  __syncthreads();
+  // stash (coalesced along columns)
+  if (st_gates)
+    for (int e = tid; e < nrows * GH; e += NT) { const int r = e / GH, j = e - r * GH; st_gates[(size_t)r * GH + j] = S[r * pS + j]; }
+  if (st_ahn && gru)
+    for (int e = tid; e < nrows * H; e += NT) { const int r = e / H, j = e - r * H; st_ahn[(size_t)r * H + j] = ahn[r * pH + j]; }
+  if (st_h)
+    for (int e = tid; e < nrows * H; e += NT) { const int r = e / H, j = e - r * H; st_h[(size_t)r * H + j] = hp[j * RS + r]; }
+  if (st_c && !gru)
+    for (int e = tid; e < nrows * H; e += NT) { const int r = e / H, j = e - r * H; st_c[(size_t)r * H + j] = cp[j * RS + r]; }
+  // LinearZeros (modules.py:93-95)
+  tile_gemm<RPT>(hp, w.WfT, d.Cop, H, d.Co, sm + sp.wst, [&](int r, int j, float v) {
+    orow[r * pO + j] = (v + w.bf[j]) * expf(3.0f * w.lf[j]);
+  });
+  __syncthreads();
+  if (st_o)
+    for (int e = tid; e < nrows * d.Co; e += NT) { const int r = e / d.Co, j = e - r * d.Co; st_o[(size_t)r * d.Co + j] = orow[r * pO + j]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int RPT>
+__global__ void __launch_bounds__(NT) core_fwd_wave(FwdArgs a, int wave, int kmin) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int R = Tile<RPT>::R, RS = Tile<RPT>::RS;
+  const Dims &d = a.d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = kmin + blockIdx.y, t = wave - k;
+  const int row0 = blockIdx.x * R, nrows = min(R, a.B - row0);
+  const int C = d.C, Ci = d.Ci, Cz = d.Cz, H = d.H, B = a.B;
+  const SmemPlan sp = plan_smem(d, R, false, false);
+  const StepWeights w = a.dv.step(d, k);
+  const size_t cell = (size_t)k * a.Tp + t;
+  const int pC = odd(C), pO = odd(d.Co > C ? d.Co : C);
+  float *xs = sm + sp.xs, *zact = sm + sp.zact, *zrow = sm + sp.zrow, *hp = sm + sp.hp, *cp = sm + sp.cp;
+
+  // 1. ActNorm (modules.py:45-66): y = (x + bias) * exp(logs)
+  for (int e = tid; e < R * C; e += NT) {
+    const int r = e / C, c = e - r * C;
+    float v = 0.f;
+    if (r < nrows) {
+      const int b = row0 + r;
+      const float x = (k == a.k_first) ? a.x0[(size_t)b * a.x_sb + (size_t)t * a.x_st + c]
+                                       : a.xin[(cell * B + b) * C + c];
+      v = (x + w.an_bias[c]) * expf(w.an_logs[c]);
+      if (a.st_y) a.st_y[(cell * B + b) * C + c] = v;
+    }
+    xs[c * RS + r] = v;
+  }
+  for (int e = tid; e < R * H; e += NT) {
+    const int r = e / H, m = e - r * H;
+    float hv = 0.f, cv = 0.f;
+    if (r < nrows) {
+      const int b = row0 + r;
+      if (t > 0) {
+        hv = a.st_h[((cell - 1) * B + b) * H + m];
+        if (d.G == 4) cv = a.st_c[((cell - 1) * B + b) * H + m];
+      } else {
+        if (a.h0) hv = a.h0[((size_t)k * B + b) * H + m];
+        if (d.G == 4 && a.c0) cv = a.c0[((size_t)k * B + b) * H + m];
+      }
+    }
+    hp[m * RS + r] = hv;
+    if (d.G == 4) cp[m * RS + r] = cv;
+  }
+  // 2. invertible 1x1 conv (modules.py:186): z = y @ W
+  tile_gemm<RPT>(xs, w.Wfwd, d.Cp, C, C, sm + sp.wst, [&](int r, int j, float v) {
+    zrow[r * pC + j] = v;
+    if (j < Ci) zact[j * RS + r] = v;
+  });
+  __syncthreads();
+  if (a.st_zf)
+    for (int e = tid; e < nrows * C; e += NT) { const int r = e / C, j = e - r * C; a.st_zf[(cell * B + row0 + r) * C + j] = zrow[r * pC + j]; }
+
+  // 3. coupling network
+  const size_t rowbase = cell * B + row0;
+  coupling_net<RPT>(d, w, sp, sm, nrows, a.G + ((size_t)t * B + row0) * a.g_ld + (size_t)(k - a.g_k0) * d.GH, a.g_ld,
+                    a.st_gates ? a.st_gates + rowbase * d.GH : nullptr, a.st_ahn ? a.st_ahn + rowbase * H : nullptr,
+                    a.st_h + rowbase * H, a.st_c ? a.st_c + rowbase * H : nullptr,
+                    a.st_o ? a.st_o + rowbase * d.Co : nullptr);
+
+  // 4. coupling (models.py:331-341), log-det, NLL on the last step (modules.py:207-212, models.py:563-565)
+  const float *orow = sm + sp.orow;
+  const bool last = (k == a.k_last);
+  for (int r = warp; r < nrows; r += NT / 32) {
+    const int b = row0 + r;
+    float lsum = 0.f;
+    for (int q = lane; q < Cz; q += 32) {
+      const float z2 = zrow[r * pC + Ci + q];
+      if (d.affine) {
+        const float shift = orow[r * pO + 2 * q], sc = orow[r * pO + 2 * q + 1];
+        const float s = fmaxf(sigmoidf_(sc + 2.0f), d.eps);
+        zrow[r * pC + Ci + q] = (z2 + shift) * s;
+        lsum += logf(s);
+        if (a.scale_out) a.scale_out[((size_t)k * B + b) * Cz + q] = s;
+      } else {
+        zrow[r * pC + Ci + q] = z2 + orow[r * pO + q];
+      }
+    }
+    lsum = warp_sum(lsum);
+    __syncwarp();
+    float ld = lsum;
+    if (k != a.k_first || a.ld_accumulate) ld += a.ld[(size_t)t * B + b];
+    if (last && a.nll) {
+      float zsq = 0.f;
+      for (int c = lane; c < C; c += 32) { const float z = zrow[r * pC + c]; zsq += z * z; }
+      zsq = warp_sum(zsq);
+      if (lane == 0) a.nll[(size_t)t * B + b] = -(ld - 0.5f * (zsq + (float)C * kLog2Pi)) / kLn2;
+    }
+    if (lane == 0) a.ld[(size_t)t * B + b] = ld;
+  }
+  __syncthreads();
+  float *dst = last ? a.z_out + (size_t)t * B * C : a.xin + (cell + a.Tp) * B * C;  // XIN[k+1][t]
+  for (int e = tid; e < nrows * C; e += NT) { const int r = e / C, j = e - r * C; dst[(size_t)(row0 + r) * C + j] = zrow[r * pC + j]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent inverse kernel: one CTA per sequence tile, all frames of a chunk x all K steps.
+template <int RPT>
+__global__ void __launch_bounds__(NT) core_inv_persistent(InvArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int R = Tile<RPT>::R, RS = Tile<RPT>::RS;
+  const Dims &d = a.d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = blockIdx.x * R, nrows = min(R, a.B - row0);
+  const int C = d.C, Ci = d.Ci, Cz = d.Cz, H = d.H, B = a.B, GH = d.GH, D = d.D;
+  const bool ar = a.cstatic != nullptr;
+  const SmemPlan sp = plan_smem(d, R, false, ar);
+  const int pC = odd(C), pO = odd(d.Co > C ? d.Co : C), pS = odd(GH);
+  float *xs = sm + sp.xs, *zact = sm + sp.zact, *zrow = sm + sp.zrow, *hp = sm + sp.hp, *cp = sm + sp.cp;
+  float *S = sm + sp.S, *cact = sm + sp.cact, *hist = sm + sp.hist, *ldacc = sm + sp.ldacc;
+  const int hist0 = d.Far / C;  // p1_face history length
+
+  // AR window (models.py:602): ring of hist0 frame slots; slot `head` holds the oldest frame.
+  int head = 0;
+  if (ar) {
+    for (int e = tid; e < R * d.Far; e += NT) {
+      const int r = e / d.Far, i = e - r * d.Far;
+      const int s = i / C, c = i - s * C;
+      float v = 0.f;
+      if (r < nrows) v = a.faces[(size_t)(row0 + r) * a.f_sb + (size_t)(a.t_abs0 - hist0 + s) * a.f_st + c];
+      hist[i * RS + r] = v;
+    }
+  }
+  __syncthreads();
+
+  for (int tc = 0; tc < a.Tc; ++tc) {
+    // latent for this frame (GaussianDiag.sample output, models.py:511) or the given z (invert)
+    for (int e = tid; e < R * C; e += NT) {
+      const int r = e / C, c = e - r * C;
+      float v = 0.f;
+      if (r < nrows && a.noise) v = a.noise[((size_t)(a.t_rel0 + tc) * B + row0 + r) * C + c];
+      zrow[r * pC + c] = v;
+      if (c < Ci) zact[c * RS + r] = v;
+    }
+    if (tid < R) ldacc[tid] = 0.f;
+    __syncthreads();
+    for (int k = a.k_hi; k >= a.k_lo; --k) {
+      const StepWeights w = a.dv.step(d, k);
+      for (int e = tid; e < R * H; e += NT) {
+        const int r = e / H, m = e - r * H;
+        float hv = 0.f, cv = 0.f;
+        if (r < nrows) {
+          hv = a.hstate[((size_t)k * B + row0 + r) * H + m];
+          if (d.G == 4) cv = a.cstate[((size_t)k * B + row0 + r) * H + m];
+        }
+        hp[m * RS + r] = hv;
+        if (d.G == 4) cp[m * RS + r] = cv;
+      }
+      const float *Grow = nullptr;
+      if (ar) {
+        // cond_transform (models.py:187-190) = static columns (precomputed, incl. bias) + autoregressive
+        // p1_face window columns; then the c-part of the gate-ih product.
+        const float *cs = a.cstatic + ((size_t)tc * B + row0) * a.cs_ld + (size_t)k * D;
+        tile_gemm<RPT>(hist, w.WcArT, D, d.Far, D, sm + sp.wst, [&](int r, int j, float v) {
+          v += (r < nrows) ? cs[(size_t)r * a.cs_ld + j] : 0.f;
+          cact[j * RS + r] = v > 0.f ? v : kLeaky * v;
+        }, (hist0 - head) * C, head * C - d.Far, head * C);
+        tile_gemm<RPT>(cact, w.WihCT, GH, D, GH, sm + sp.wst, [&](int r, int j, float v) { S[r * pS + j] = v + w.b_ih[j]; });
+      } else {
+        Grow = a.G + ((size_t)tc * B + row0) * a.g_ld + (size_t)(k - a.g_k0) * GH;
+      }
+      coupling_net<RPT>(d, w, sp, sm, nrows, Grow, a.g_ld, nullptr, nullptr,
+                        a.hstate + ((size_t)k * B + row0) * H, d.G == 4 ? a.cstate + ((size_t)k * B + row0) * H : nullptr,
+                        nullptr);
+      // inverse coupling (models.py:358-366): z2 = z2 / scale - shift
+      const float *orow = sm + sp.orow;
+      for (int r = warp; r < R; r += NT / 32) {
+        float lsum = 0.f;
+        for (int q = lane; q < Cz; q += 32) {
+          const float z2 = zrow[r * pC + Ci + q];
+          float v;
+          if (d.affine) {
+            const float shift = orow[r * pO + 2 * q], sc = orow[r * pO + 2 * q + 1];
+            const float s = fmaxf(sigmoidf_(sc + 2.0f), d.eps);
+            v = z2 / s - shift;
+            lsum += logf(s);
+          } else {
+            v = z2 - orow[r * pO + q];
+          }
+          xs[(Ci + q) * RS + r] = v;
+        }
+        for (int c = lane; c < Ci; c += 32) xs[c * RS + r] = zrow[r * pC + c];
+        lsum = warp_sum(lsum);
+        if (lane == 0) ldacc[r] -= lsum;
+      }
+      // 1x1 conv inverse then ActNorm inverse (modules.py:175-177, 189-193, 76-78)
+      tile_gemm<RPT>(xs, w.Winv, d.Cp, C, C, sm + sp.wst, [&](int r, int j, float v) {
+        const float x = v * expf(-w.an_logs[j]) - w.an_bias[j];
+        zrow[r * pC + j] = x;
+        if (j < Ci) zact[j * RS + r] = x;
+      });
+      __syncthreads();
+    }
+    // emit the frame, slide the autoregressive window
+    const int t_abs = a.t_abs0 + tc;
+    for (int e = tid; e < nrows * C; e += NT) {
+      const int r = e / C, c = e - r * C;
+      a.faces_out[(size_t)(row0 + r) * a.fo_sb + (size_t)t_abs * a.fo_st + c] = zrow[r * pC + c];
+    }
+    if (a.logdet_out && tid < nrows) a.logdet_out[(size_t)(a.t_rel0 + tc) * B + row0 + tid] = ldacc[tid];
+    if (ar) {
+      for (int e = tid; e < R * C; e += NT) {
+        const int r = e / C, c = e - r * C;
+        hist[(head * C + c) * RS + r] = zrow[r * pC + c];
+      }
+      head = (head + 1) % hist0;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+
+constexpr int kMaxSmem = 227 * 1024;
+
+int fwd_smem_bytes(const Dims &d, int R) { return plan_smem(d, R, false, false).total * (int)sizeof(float); }
+
+// Rows per CTA = 4*RPT.  Larger tiles amortise the weight stream, smaller tiles expose more CTAs;
+// take the largest tile that still gives every SM a CTA (LFI_RPT overrides for experiments).
+int choose_rpt(const Dims &d, int B, bool bwd, bool sampler) {
+  int forced = 0;
+  if (const char *e = getenv(sampler ? "LFI_RPT_SAMPLE" : (bwd ? "LFI_RPT_BWD" : "LFI_RPT"))) forced = atoi(e);
+  const int cand[4] = {8, 4, 2, 1};
+  int best = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int rpt = cand[i], R = RG * rpt;
+    const int bytes = plan_smem(d, R, bwd, sampler).total * (int)sizeof(float);
+    if (bytes > kMaxSmem) continue;
+    if (forced == rpt) return rpt;
+    const long ctas = (long)((B + R - 1) / R) * (sampler ? 1 : d.K);
+    best = rpt;
+    if (ctas >= (sampler ? 120 : 148)) return rpt;
+  }
+  return best;  // smallest tile that fits (0 = nothing fits)
+}
+
+template <int RPT> static int launch_fwd_t(const FwdArgs &a, cudaStream_t st) {
+  constexpr int R = Tile<RPT>::R;
+  const int bytes = plan_smem(a.d, R, false, false).total * (int)sizeof(float);
+  LFI_CUDA(cudaFuncSetAttribute(core_fwd_wave<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  const int tiles = (a.B + R - 1) / R;
+  const int nk = a.k_last - a.k_first + 1;
+  for (int wave = 0; wave < a.Tp + nk - 1; ++wave) {
+    // active steps: k_first + i with 0 <= wave - i < Tp
+    const int i0 = max(0, wave - a.Tp + 1), i1 = min(nk - 1, wave);
+    dim3 grid(tiles, i1 - i0 + 1);
+    core_fwd_wave<RPT><<<grid, NT, bytes, st>>>(a, wave + a.k_first, a.k_first + i0);
+  }
+  LFI_LAUNCH_CHECK_N(a.Tp + nk - 1);
+  return LFI_OK;
+}
+
+int launch_fwd(const FwdArgs &a, cudaStream_t st) {
+  const int rpt = choose_rpt(a.d, a.B, false, false);
+  switch (rpt) {
+    case 8: return launch_fwd_t<8>(a, st);
+    case 4: return launch_fwd_t<4>(a, st);
+    case 2: return launch_fwd_t<2>(a, st);
+    case 1: return launch_fwd_t<1>(a, st);
+  }
+  set_error("flow core: shape does not fit shared memory (H=%d G=%d C=%d)", a.d.H, a.d.G, a.d.C);
+  return LFI_ERR_SHAPE;
+}
+
+template <int RPT> static int launch_inv_t(const InvArgs &a, cudaStream_t st) {
+  constexpr int R = Tile<RPT>::R;
+  const int bytes = plan_smem(a.d, R, false, a.cstatic != nullptr).total * (int)sizeof(float);
+  LFI_CUDA(cudaFuncSetAttribute(core_inv_persistent<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  core_inv_persistent<RPT><<<(a.B + R - 1) / R, NT, bytes, st>>>(a);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+int launch_inv(const InvArgs &a, cudaStream_t st) {
+  const int rpt = choose_rpt(a.d, a.B, false, true);
+  switch (rpt) {
+    case 8: return launch_inv_t<8>(a, st);
+    case 4: return launch_inv_t<4>(a, st);
+    case 2: return launch_inv_t<2>(a, st);
+    case 1: return launch_inv_t<1>(a, st);
+  }
+  set_error("flow sampler: shape does not fit shared memory (H=%d D=%d C=%d)", a.d.H, a.d.D, a.d.C);
+  return LFI_ERR_SHAPE;
+}
+
+}  // namespace core
+}  // namespace lfi

@@ -1,0 +1,628 @@
+// Host-side orchestration of the hot path behind the C ABI (include/lfi_b200.h):
+//   lfi_derive            derived weight cache
+//   lfi_seq_train_fwd/bwd SeqGlow.forward (models.py:534-561) and its backward
+//   lfi_seq_sample        SeqGlow.inference / SeqGlow.invert (models.py:567-645)
+//   lfi_flowstep          FlowStep.forward on one frame (models.py:305-373)
+//   lfi_invconv_compose   InvertibleConv1x1.get_weight (modules.py:149-178) and its chain rule
+// Time-parallel work (encoders, cond_transform, gate-ih, all weight gradients) goes through
+// gemm_dispatch; the sequential recurrences go through the flow-core kernels.
+#include "aux_kernels.cuh"
+#include "core_api.cuh"
+
+namespace lfi {
+
+// ------------------------------------------------------------------------------------------------
+// derived cache layout (floats)
+struct DerivedLayout {
+  size_t Wfwd, WT, Winv, WzT, WihZ, WhhT, WfT, WcArT, WihCT, WcF, total;
+};
+static DerivedLayout derived_layout(const Dims &d) {
+  DerivedLayout L;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += round_up_sz(n, 64); return r; };
+  const size_t K = d.K;
+  L.Wfwd = take(K * d.C * d.Cp);
+  L.WT = take(K * d.C * d.Cp);
+  L.Winv = take(K * d.C * d.Cp);
+  L.WzT = take(K * d.Ci * d.GH);
+  L.WihZ = take(K * d.GH * d.Cip);
+  L.WhhT = take(K * d.H * d.GH);
+  L.WfT = take(K * d.H * d.Cop);
+  L.WcArT = take(K * d.Far * d.D);
+  L.WihCT = take(K * d.D * d.GH);
+  L.WcF = take(K * d.D * d.Fe);
+  L.total = o;
+  return L;
+}
+
+static core::DerivedView make_view(const Dims &d, const void *derived, const lfi_params *p) {
+  const DerivedLayout L = derived_layout(d);
+  const float *base = (const float *)derived;
+  core::DerivedView v;
+  v.an_bias = p->an_bias; v.an_logs = p->an_logs;
+  v.Wfwd = base + L.Wfwd; v.WT = base + L.WT; v.Winv = base + L.Winv;
+  v.WzT = base + L.WzT; v.WihZ = base + L.WihZ; v.WhhT = base + L.WhhT; v.Whh = p->w_hh;
+  v.b_ih = p->b_ih; v.b_hh = p->b_hh; v.WfT = base + L.WfT; v.Wf = p->wf; v.bf = p->bf; v.lf = p->lf;
+  v.WcArT = base + L.WcArT; v.WihCT = base + L.WihCT;
+  return v;
+}
+
+static int derive_impl(const lfi_shape *s, const lfi_params *p, const float *winv, void *derived, cudaStream_t st) {
+  Dims d;
+  LFI_TRY(make_dims(s, &d));
+  LFI_REQUIRE(p && derived, LFI_ERR_ARG, "lfi_derive: null argument");
+  const DerivedLayout L = derived_layout(d);
+  float *base = (float *)derived;
+  const int K = d.K, C = d.C, Ci = d.Ci, GH = d.GH, H = d.H, D = d.D, Co = d.Co, In = Ci + D;
+  LFI_TRY(aux::gather2d(base + L.Wfwd, d.Cp, p->w, (long)C * C, C, 1, K, C, C, st));
+  LFI_TRY(aux::gather2d(base + L.WT, d.Cp, p->w, (long)C * C, 1, C, K, C, C, st));
+  if (winv) LFI_TRY(aux::gather2d(base + L.Winv, d.Cp, winv, (long)C * C, C, 1, K, C, C, st));
+  LFI_TRY(aux::gather2d(base + L.WzT, GH, p->w_ih, (long)GH * In, 1, In, K, Ci, GH, st));
+  LFI_TRY(aux::gather2d(base + L.WihZ, d.Cip, p->w_ih, (long)GH * In, In, 1, K, GH, Ci, st));
+  LFI_TRY(aux::gather2d(base + L.WhhT, GH, p->w_hh, (long)GH * H, 1, H, K, H, GH, st));
+  LFI_TRY(aux::gather2d(base + L.WfT, d.Cop, p->wf, (long)Co * H, 1, H, K, H, Co, st));
+  LFI_TRY(aux::gather2d(base + L.WcArT, D, p->wc, (long)D * d.F, 1, d.F, K, d.Far, D, st));
+  LFI_TRY(aux::gather2d(base + L.WihCT, GH, p->w_ih + Ci, (long)GH * In, 1, In, K, D, GH, st));
+  LFI_TRY(aux::fold_wc(base + L.WcF, p->wc, d, *s, st));
+  return LFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace layouts
+struct EncWs {
+  float *xp;     // [B*Tx][3E]
+  float *hs;     // [hist][M][E]   (training) or [2][M][E] ping-pong (sampling)
+  float *gates;  // [hist][M][3E]  (training only)
+  float *ahn;    // [hist][M][E]   (training only)
+};
+struct TrainWs {
+  float *cond, *Cact, *G, *ld, *gh;
+  EncWs enc[LFI_NMOD];
+  core::Stash st;
+  // backward
+  float *dx, *dh, *dc, *dG, *dAh, *dO, *dzf, *dC, *dcond, *dWcF, *xg, *dhe, *dai, *dah;
+  size_t bytes;
+};
+
+static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, void *ws, TrainWs *w) {
+  Bump b(ws, 0);
+  const size_t Tp = T - d.start_ts, M = Tp * B, K = d.K;
+  w->cond = b.take<float>(M * d.Fe);
+  w->Cact = b.take<float>(M * K * d.D);
+  w->G = b.take<float>(M * K * d.GH);
+  w->ld = b.take<float>(M);
+  size_t ghmax = 0, xgmax = 0, emax = 0;
+  for (int m = 0; m < LFI_NMOD; ++m) {
+    w->enc[m] = EncWs{nullptr, nullptr, nullptr, nullptr};
+    if (s->hist[m] <= 0 || s->ehid[m] <= 0) continue;
+    const size_t E = s->ehid[m], h = s->hist[m];
+    w->enc[m].xp = b.take<float>((size_t)B * T * 3 * E);
+    w->enc[m].hs = b.take<float>(h * M * E);
+    w->enc[m].gates = b.take<float>(h * M * 3 * E);
+    w->enc[m].ahn = b.take<float>(h * M * E);
+    if (M * 3 * E > ghmax) ghmax = M * 3 * E;
+    if (h * M * s->dim[m] > xgmax) xgmax = h * M * s->dim[m];
+    if (E > emax) emax = E;
+  }
+  w->gh = b.take<float>(ghmax);
+  const size_t cells = K * M;
+  w->st.y = b.take<float>(cells * d.C);
+  w->st.zf = b.take<float>(cells * d.C);
+  w->st.h = b.take<float>(cells * d.H);
+  w->st.c = d.G == 4 ? b.take<float>(cells * d.H) : nullptr;
+  w->st.gates = b.take<float>(cells * d.GH);
+  w->st.ahn = d.G == 3 ? b.take<float>(cells * d.H) : nullptr;
+  w->st.o = b.take<float>(cells * d.Co);
+  w->st.xin = b.take<float>((cells + M) * d.C);
+  // backward
+  w->dx = b.take<float>(cells * d.C);
+  w->dh = b.take<float>(cells * d.H);
+  w->dc = d.G == 4 ? b.take<float>(cells * d.H) : nullptr;
+  w->dG = b.take<float>(M * K * d.GH);
+  w->dAh = b.take<float>(cells * d.GH);
+  w->dO = b.take<float>(cells * d.Co);
+  w->dzf = b.take<float>(cells * d.C);
+  w->dC = b.take<float>(M * K * d.D);
+  w->dcond = b.take<float>(M * d.Fe);
+  w->dWcF = b.take<float>(K * d.D * d.Fe);
+  w->xg = b.take<float>(xgmax);
+  w->dhe = b.take<float>(M * emax);
+  w->dai = b.take<float>(ghmax);
+  w->dah = b.take<float>(ghmax);
+  w->bytes = round_up_sz(b.off, 256);
+}
+
+// Encoders + "enc: none" windows into the folded feature matrix cond[M][Fe] for frames
+// t = t0 .. t0+Tp-1 (ModalityEncoder / FeatureEncoder, models.py:55-80, 127-145).
+//   x stream m: [B][Tx][dim] ;  skip_p1: leave the p1_face columns alone (autoregressive sampler)
+//   stash != 0: keep every step's h / gates / ahn (training); else ping-pong h
+static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, const lfi_batch *bt, int t0, int Tp,
+                      float *cond, EncWs *enc, float *gh, bool stash, bool skip_p1, bool project, int mode, void *gws,
+                      size_t gws_bytes, cudaStream_t st) {
+  const int B = bt->B, T = bt->T;
+  const size_t M = (size_t)Tp * B;
+  for (int m = 0; m < LFI_NMOD; ++m) {
+    const int hist = s->hist[m];
+    if (hist <= 0) continue;
+    if (m == 0 && skip_p1) continue;
+    LFI_REQUIRE(bt->x[m], LFI_ERR_ARG, "batch: modality %d missing", m);
+    const int dim = s->dim[m], E = s->ehid[m];
+    if (E == 0) {
+      LFI_TRY(aux::gather_windows(cond + d.enc_offe[m], d.Fe, 0, bt->x[m], bt->mask[m], B, T, dim, hist, m == 0 ? 0 : 1, t0, Tp, st));
+      continue;
+    }
+    // input projection for every raw frame (window independent): xp = x @ W_ih^T
+    if (project) {
+      GemmArgs g = gemm_args(0, 1, B * T, 3 * E, dim, bt->x[m], dim, p->enc_w_ih[m], dim, enc[m].xp, 3 * E);
+      LFI_TRY(gemm_dispatch(mode, g, gws, gws_bytes, st));
+    }
+    for (int sidx = 0; sidx < hist; ++sidx) {
+      float *hprev = nullptr, *hcur;
+      if (stash) { hcur = enc[m].hs + (size_t)sidx * M * E; if (sidx) hprev = enc[m].hs + (size_t)(sidx - 1) * M * E; }
+      else { hcur = enc[m].hs + (size_t)(sidx & 1) * M * E; if (sidx) hprev = enc[m].hs + (size_t)((sidx - 1) & 1) * M * E; }
+      if (sidx) {
+        GemmArgs gg = gemm_args(0, 1, (int)M, 3 * E, E, hprev, E, p->enc_w_hh[m], E, gh, 3 * E);
+        LFI_TRY(gemm_dispatch(mode, gg, gws, gws_bytes, st));
+      }
+      aux::EncStep a;
+      a.xp = enc[m].xp; a.gh = sidx ? gh : nullptr; a.b_ih = p->enc_b_ih[m]; a.b_hh = p->enc_b_hh[m];
+      a.mask = bt->mask[m]; a.hprev = hprev; a.h = hcur;
+      a.gates = stash ? enc[m].gates + (size_t)sidx * M * 3 * E : nullptr;
+      a.ahn = stash ? enc[m].ahn + (size_t)sidx * M * E : nullptr;
+      a.cond = (sidx == hist - 1) ? cond + d.enc_offe[m] : nullptr; a.cond_ld = d.Fe;
+      a.s = sidx; a.hist = hist; a.B = B; a.T = T; a.Tp = Tp; a.t0 = t0; a.E = E;
+      LFI_TRY(aux::enc_gate_fwd(a, st));
+    }
+  }
+  return LFI_OK;
+}
+
+// cond_transform for all K steps, then the c-part of the gate-ih product (models.py:187-190, 206-208)
+static int cond_to_gates(const Dims &d, const lfi_params *p, const float *WcF, const float *cond, size_t M, float *Cact,
+                         float *G, int mode, void *gws, size_t gws_bytes, cudaStream_t st) {
+  const int K = d.K, D = d.D, GH = d.GH, In = d.Ci + D;
+  GemmArgs g = gemm_args(0, 1, (int)M, K * D, d.Fe, cond, d.Fe, WcF, d.Fe, Cact, K * D, LFI_EPI_BIAS | LFI_EPI_LRELU, p->bc);
+  LFI_TRY(gemm_dispatch(mode, g, gws, gws_bytes, st));
+  GemmArgs h = gemm_args(0, 1, (int)M, GH, D, Cact, K * D, p->w_ih + d.Ci, In, G, K * GH, LFI_EPI_BIAS, p->b_ih);
+  h.batch = K; h.sA = D; h.sB = (long)GH * In; h.sC = GH; h.sBias = GH;
+  LFI_TRY(gemm_dispatch(mode, h, gws, gws_bytes, st));
+  return LFI_OK;
+}
+
+static int check_batch(const lfi_shape *s, const Dims &d, const lfi_batch *b, int min_T) {
+  LFI_REQUIRE(b && b->B >= 1, LFI_ERR_ARG, "batch: B must be >= 1");
+  LFI_REQUIRE(b->T >= min_T, LFI_ERR_SHAPE, "batch: T=%d shorter than needed (%d)", b->T, min_T);
+  (void)s; (void)d;
+  return LFI_OK;
+}
+
+}  // namespace lfi
+
+using namespace lfi;
+
+extern "C" {
+
+int lfi_feature_dim(const lfi_shape *s) { Dims d; return make_dims(s, &d) == LFI_OK ? d.F : -1; }
+int lfi_feature_dim_folded(const lfi_shape *s) { Dims d; return make_dims(s, &d) == LFI_OK ? d.Fe : -1; }
+int lfi_start_ts(const lfi_shape *s) { Dims d; return make_dims(s, &d) == LFI_OK ? d.start_ts : -1; }
+int lfi_coupling_out(const lfi_shape *s) { Dims d; return make_dims(s, &d) == LFI_OK ? d.Co : -1; }
+
+size_t lfi_derived_bytes(const lfi_shape *s) {
+  Dims d;
+  if (make_dims(s, &d) != LFI_OK) return 0;
+  return derived_layout(d).total * sizeof(float);
+}
+
+int lfi_derive(const lfi_shape *s, const lfi_params *p, const float *winv, void *derived, int gemm_mode, void *stream) {
+  (void)gemm_mode;
+  return derive_impl(s, p, winv, derived, (cudaStream_t)stream);
+}
+
+size_t lfi_gemm_ws_bytes(void);
+
+size_t lfi_train_ws_bytes(const lfi_shape *s, int B, int T) {
+  Dims d;
+  if (make_dims(s, &d) != LFI_OK || T <= d.start_ts || B < 1) return 0;
+  TrainWs w;
+  plan_train(s, d, B, T, nullptr, &w);
+  return w.bytes + lfi_gemm_ws_bytes();
+}
+
+int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params *p, const lfi_batch *bt, float *z,
+                      float *nll, float *scale_out, void *ws, size_t ws_bytes, int gemm_mode, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d;
+  LFI_TRY(make_dims(s, &d));
+  LFI_REQUIRE(derived && p && z && nll && ws, LFI_ERR_ARG, "lfi_seq_train_fwd: null argument");
+  LFI_TRY(check_batch(s, d, bt, d.start_ts + 1));
+  const int B = bt->B, T = bt->T, Tp = T - d.start_ts;
+  const size_t M = (size_t)Tp * B;
+  TrainWs w;
+  plan_train(s, d, B, T, ws, &w);
+  LFI_REQUIRE(ws_bytes >= w.bytes + lfi_gemm_ws_bytes(), LFI_ERR_WORKSPACE, "train workspace too small: %zu < %zu", ws_bytes,
+              w.bytes + lfi_gemm_ws_bytes());
+  void *gws = (char *)ws + w.bytes;
+  const size_t gws_bytes = ws_bytes - w.bytes;
+  const DerivedLayout L = derived_layout(d);
+  const float *WcF = (const float *)derived + L.WcF;
+
+  LFI_TRY(build_cond(s, d, p, bt, d.start_ts, Tp, w.cond, w.enc, w.gh, true, false, true, gemm_mode, gws, gws_bytes, st));
+  LFI_TRY(cond_to_gates(d, p, WcF, w.cond, M, w.Cact, w.G, gemm_mode, gws, gws_bytes, st));
+
+  core::FwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = d; a.dv = make_view(d, derived, p); a.B = B; a.Tp = Tp; a.k_first = 0; a.k_last = d.K - 1;
+  a.x0 = bt->x[0] + (size_t)d.start_ts * d.C; a.x_sb = (long)T * d.C; a.x_st = d.C;
+  a.G = w.G; a.g_ld = (long)d.K * d.GH; a.g_k0 = 0;
+  a.xin = w.st.xin; a.st_y = w.st.y; a.st_zf = w.st.zf; a.st_h = w.st.h; a.st_c = w.st.c; a.st_gates = w.st.gates;
+  a.st_ahn = w.st.ahn; a.st_o = w.st.o; a.ld = w.ld; a.ld_accumulate = 0; a.nll = nll; a.z_out = z;
+  a.scale_out = scale_out;
+  return core::launch_fwd(a, st);
+}
+
+int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params *p, const lfi_batch *bt, const float *z,
+                      const float *dnll, lfi_params *g, void *ws, size_t ws_bytes, int gemm_mode, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d;
+  LFI_TRY(make_dims(s, &d));
+  LFI_REQUIRE(derived && p && z && dnll && g && ws, LFI_ERR_ARG, "lfi_seq_train_bwd: null argument");
+  LFI_TRY(check_batch(s, d, bt, d.start_ts + 1));
+  const int B = bt->B, T = bt->T, Tp = T - d.start_ts, K = d.K, C = d.C, Ci = d.Ci, GH = d.GH, H = d.H, D = d.D, Co = d.Co;
+  const int In = Ci + D;
+  const size_t M = (size_t)Tp * B;
+  TrainWs w;
+  plan_train(s, d, B, T, ws, &w);
+  LFI_REQUIRE(ws_bytes >= w.bytes + lfi_gemm_ws_bytes(), LFI_ERR_WORKSPACE, "train workspace too small");
+  void *gws = (char *)ws + w.bytes;
+  const size_t gws_bytes = ws_bytes - w.bytes;
+  const DerivedLayout L = derived_layout(d);
+  const float *WcF = (const float *)derived + L.WcF;
+
+  // 1. sequential core, reverse wavefronts
+  core::BwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = d; a.dv = make_view(d, derived, p); a.B = B; a.Tp = Tp; a.dnll = dnll; a.z = z; a.st = w.st;
+  a.dx = w.dx; a.dh = w.dh; a.dc = w.dc; a.dG = w.dG; a.dAh = w.dAh; a.dO = w.dO; a.dzf = w.dzf;
+  a.g_an_bias = g->an_bias; a.g_an_logs = g->an_logs; a.g_b_hh = g->b_hh; a.g_bf = g->bf; a.g_lf = g->lf;
+  LFI_TRY(core::launch_bwd(a, st));
+
+  // 2. weight gradients of the per-step matrices as batched (over k) reductions over the M rows
+  auto wgrad = [&](int Mo, int No, size_t red, const float *A, int lda, long sA, const float *Bm, int ldb, long sB, float *Cm,
+                   int ldc, long sC) -> int {
+    GemmArgs q = gemm_args(1, 0, Mo, No, (int)red, A, lda, Bm, ldb, Cm, ldc, LFI_EPI_ACCUM);
+    q.batch = K; q.sA = sA; q.sB = sB; q.sC = sC;
+    return gemm_dispatch(gemm_mode, q, gws, gws_bytes, st);
+  };
+  if (Tp > 1)  // dW_hh[k] += dA_h[k][t>=1]^T h[k][t-1]
+    LFI_TRY(wgrad(GH, H, (size_t)(Tp - 1) * B, w.dAh + (size_t)B * GH, GH, (long)(M * GH), w.st.h, H, (long)(M * H), g->w_hh, H,
+                  (long)GH * H));
+  LFI_TRY(wgrad(GH, Ci, M, w.dG, K * GH, GH, w.st.zf, C, (long)(M * C), g->w_ih, In, (long)GH * In));       // dW_ih[:, :Ci]
+  LFI_TRY(wgrad(GH, D, M, w.dG, K * GH, GH, w.Cact, K * D, D, g->w_ih + Ci, In, (long)GH * In));           // dW_ih[:, Ci:]
+  LFI_TRY(wgrad(Co, H, M, w.dO, Co, (long)(M * Co), w.st.h, H, (long)(M * H), g->wf, H, (long)Co * H));     // dWf
+  LFI_TRY(wgrad(C, C, M, w.st.y, C, (long)(M * C), w.dzf, C, (long)(M * C), g->w, C, (long)C * C));         // dW (1x1 conv)
+  LFI_TRY(aux::colsum(g->b_ih, w.dG, K * GH, (int)M, K * GH, 1.0f, st));
+
+  // 3. cond_transform backward
+  {
+    GemmArgs q = gemm_args(0, 0, (int)M, D, GH, w.dG, K * GH, p->w_ih + Ci, In, w.dC, K * D, LFI_EPI_LRELU_BWD);
+    q.batch = K; q.sA = GH; q.sB = (long)GH * In; q.sC = D; q.aux = w.Cact; q.ldaux = K * D; q.sAux = D;
+    LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
+    LFI_TRY(aux::colsum(g->bc, w.dC, K * D, (int)M, K * D, 1.0f, st));
+    GemmArgs r = gemm_args(1, 0, K * D, d.Fe, (int)M, w.dC, K * D, w.cond, d.Fe, w.dWcF, d.Fe, 0);
+    LFI_TRY(gemm_dispatch(gemm_mode, r, gws, gws_bytes, st));
+    LFI_TRY(aux::unfold_wc_grad(g->wc, w.dWcF, d, *s, st));
+  }
+  // d cond for the encoder columns only (inputs carry no gradient)
+  int enc_lo = -1;
+  for (int m = 0; m < LFI_NMOD; ++m)
+    if (s->hist[m] > 0 && s->ehid[m] > 0) { enc_lo = d.enc_offe[m]; break; }
+  if (enc_lo < 0) return LFI_OK;
+  {
+    GemmArgs q = gemm_args(0, 0, (int)M, d.Fe - enc_lo, K * D, w.dC, K * D, WcF + enc_lo, d.Fe, w.dcond + enc_lo, d.Fe, 0);
+    LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
+  }
+
+  // 4. encoder GRUs, BPTT over the window (models.py:63-64)
+  for (int m = 0; m < LFI_NMOD; ++m) {
+    const int hist = s->hist[m], E = s->ehid[m], dim = s->dim[m];
+    if (hist <= 0 || E <= 0) continue;
+    LFI_TRY(aux::gather_windows(w.xg, dim, 1, bt->x[m], bt->mask[m], B, T, dim, hist, 1, d.start_ts, Tp, st));
+    LFI_TRY(aux::fill(w.dhe, 0.f, M * E, st));
+    for (int sidx = hist - 1; sidx >= 0; --sidx) {
+      aux::EncStepBwd e;
+      e.gates = w.enc[m].gates + (size_t)sidx * M * 3 * E; e.ahn = w.enc[m].ahn + (size_t)sidx * M * E;
+      e.hprev = sidx ? w.enc[m].hs + (size_t)(sidx - 1) * M * E : nullptr;
+      e.dh = w.dhe; e.dh_extra = (sidx == hist - 1) ? w.dcond + d.enc_offe[m] : nullptr; e.dh_extra_ld = d.Fe;
+      e.dai = w.dai; e.dah = w.dah; e.M = (int)M; e.E = E;
+      LFI_TRY(aux::enc_gate_bwd(e, st));
+      LFI_TRY(aux::colsum(g->enc_b_ih[m], w.dai, 3 * E, (int)M, 3 * E, 1.0f, st));
+      LFI_TRY(aux::colsum(g->enc_b_hh[m], w.dah, 3 * E, (int)M, 3 * E, 1.0f, st));
+      GemmArgs q = gemm_args(1, 0, 3 * E, dim, (int)M, w.dai, 3 * E, w.xg + (size_t)sidx * M * dim, dim, g->enc_w_ih[m], dim, LFI_EPI_ACCUM);
+      LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
+      if (sidx) {
+        GemmArgs r = gemm_args(1, 0, 3 * E, E, (int)M, w.dah, 3 * E, e.hprev, E, g->enc_w_hh[m], E, LFI_EPI_ACCUM);
+        LFI_TRY(gemm_dispatch(gemm_mode, r, gws, gws_bytes, st));
+        GemmArgs t = gemm_args(0, 0, (int)M, E, 3 * E, w.dah, 3 * E, p->enc_w_hh[m], E, w.dhe, E, LFI_EPI_ACCUM);
+        LFI_TRY(gemm_dispatch(gemm_mode, t, gws, gws_bytes, st));
+      }
+    }
+  }
+  return LFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampling / invert
+struct SampleWs {
+  float *cond, *Cs, *G, *gh, *hstate, *cstate;
+  EncWs enc[LFI_NMOD];
+  size_t bytes;
+};
+static void plan_sample(const lfi_shape *s, const Dims &d, int B, int T, int chunk, void *ws, SampleWs *w) {
+  Bump b(ws, 0);
+  const size_t Mc = (size_t)chunk * B, K = d.K;
+  w->cond = b.take<float>(Mc * d.Fe);
+  w->Cs = b.take<float>(Mc * K * d.D);
+  w->G = b.take<float>(Mc * K * d.GH);
+  w->hstate = b.take<float>(K * B * d.H);
+  w->cstate = d.G == 4 ? b.take<float>(K * B * d.H) : nullptr;
+  size_t ghmax = 0;
+  for (int m = 0; m < LFI_NMOD; ++m) {
+    w->enc[m] = EncWs{nullptr, nullptr, nullptr, nullptr};
+    if (s->hist[m] <= 0 || s->ehid[m] <= 0) continue;
+    const size_t E = s->ehid[m];
+    w->enc[m].xp = b.take<float>((size_t)B * T * 3 * E);
+    w->enc[m].hs = b.take<float>(2 * Mc * E);
+    if (Mc * 3 * E > ghmax) ghmax = Mc * 3 * E;
+  }
+  w->gh = b.take<float>(ghmax);
+  w->bytes = round_up_sz(b.off, 256);
+}
+
+// FeatureEncoder.forward (models.py:127-145) for frames t0 .. t0+Tp-1 of a batch: folded features [Tp*B][Fe]
+size_t lfi_feature_ws_bytes(const lfi_shape *s, int B, int T, int Tp) {
+  Dims d;
+  if (make_dims(s, &d) != LFI_OK || B < 1 || Tp < 1) return 0;
+  SampleWs w;
+  plan_sample(s, d, B, T, Tp, nullptr, &w);
+  return w.bytes + lfi_gemm_ws_bytes();
+}
+
+int lfi_feature_encode(const lfi_shape *s, const lfi_params *p, const lfi_batch *bt, int t0, int Tp, float *cond, void *ws,
+                       size_t ws_bytes, int gemm_mode, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d;
+  LFI_TRY(make_dims(s, &d));
+  LFI_REQUIRE(p && bt && cond && ws, LFI_ERR_ARG, "lfi_feature_encode: null argument");
+  LFI_REQUIRE(t0 >= d.start_ts && t0 + Tp <= bt->T && Tp >= 1, LFI_ERR_SHAPE, "lfi_feature_encode: frames [%d,%d) outside [%d,%d)", t0,
+              t0 + Tp, d.start_ts, bt->T);
+  SampleWs w;
+  plan_sample(s, d, bt->B, bt->T, Tp, ws, &w);
+  LFI_REQUIRE(ws_bytes >= w.bytes + lfi_gemm_ws_bytes(), LFI_ERR_WORKSPACE, "feature workspace too small");
+  void *gws = (char *)ws + w.bytes;
+  return build_cond(s, d, p, bt, t0, Tp, cond, w.enc, w.gh, false, false, true, gemm_mode, gws, ws_bytes - w.bytes, st);
+}
+
+size_t lfi_sample_ws_bytes(const lfi_shape *s, int B, int T, int chunk) {
+  Dims d;
+  if (make_dims(s, &d) != LFI_OK || B < 1 || chunk < 1) return 0;
+  SampleWs w;
+  plan_sample(s, d, B, T, chunk, nullptr, &w);
+  return w.bytes + lfi_gemm_ws_bytes();
+}
+
+int lfi_seq_sample(const lfi_shape *s, const void *derived, const lfi_params *p, const lfi_batch *bt, int seq_len,
+                   const float *noise, float *faces, float *logdet_out, int teacher_forced, int chunk, void *ws,
+                   size_t ws_bytes, int gemm_mode, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d;
+  LFI_TRY(make_dims(s, &d));
+  LFI_REQUIRE(derived && p && faces && ws && chunk >= 1, LFI_ERR_ARG, "lfi_seq_sample: null argument");
+  LFI_TRY(check_batch(s, d, bt, seq_len));
+  LFI_REQUIRE(seq_len > d.start_ts, LFI_ERR_SHAPE, "seq_len=%d must exceed the longest history %d", seq_len, d.start_ts);
+  const int B = bt->B, T = bt->T, Tgen = seq_len - d.start_ts, K = d.K;
+  SampleWs w;
+  plan_sample(s, d, B, T, chunk, ws, &w);
+  LFI_REQUIRE(ws_bytes >= w.bytes + lfi_gemm_ws_bytes(), LFI_ERR_WORKSPACE, "sample workspace too small: %zu < %zu", ws_bytes,
+              w.bytes + lfi_gemm_ws_bytes());
+  void *gws = (char *)ws + w.bytes;
+  const size_t gws_bytes = ws_bytes - w.bytes;
+  const DerivedLayout L = derived_layout(d);
+  const float *WcF = (const float *)derived + L.WcF;
+
+  LFI_CUDA(cudaMemsetAsync(w.hstate, 0, (size_t)K * B * d.H * sizeof(float), st));
+  if (w.cstate) LFI_CUDA(cudaMemsetAsync(w.cstate, 0, (size_t)K * B * d.H * sizeof(float), st));
+
+  // the input projections of the encoders do not depend on the window: computed once (first chunk)
+  for (int c0 = 0; c0 < Tgen; c0 += chunk) {
+    const int Tc = (Tgen - c0 < chunk) ? (Tgen - c0) : chunk;
+    const size_t Mc = (size_t)Tc * B;
+    const int t0 = d.start_ts + c0;
+    LFI_TRY(build_cond(s, d, p, bt, t0, Tc, w.cond, w.enc, w.gh, false, !teacher_forced, c0 == 0, gemm_mode, gws, gws_bytes, st));
+    core::InvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.d = d; a.dv = make_view(d, derived, p); a.B = B; a.Tc = Tc; a.k_hi = K - 1; a.k_lo = 0; a.g_k0 = 0;
+    a.t_abs0 = t0; a.t_rel0 = c0; a.noise = noise;
+    if (teacher_forced) {
+      LFI_TRY(cond_to_gates(d, p, WcF, w.cond, Mc, w.Cs, w.G, gemm_mode, gws, gws_bytes, st));
+      a.G = w.G; a.g_ld = (long)K * d.GH;
+    } else {
+      // static columns of cond_transform (pre-activation, bias included); the p1_face window is added in-kernel
+      GemmArgs q = gemm_args(0, 1, (int)Mc, K * d.D, d.Fe - d.Far, w.cond + d.Far, d.Fe, WcF + d.Far, d.Fe, w.Cs, K * d.D,
+                             LFI_EPI_BIAS, p->bc);
+      if (d.Fe > d.Far) LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
+      else LFI_TRY(aux::gather2d(w.Cs, K * d.D, p->bc, 0, 0, 1, 1, (int)Mc, K * d.D, st));  // no static modality: bias only
+      a.cstatic = w.Cs; a.cs_ld = (long)K * d.D;
+      a.faces = faces; a.f_sb = (long)seq_len * d.C; a.f_st = d.C;
+    }
+    a.faces_out = faces; a.fo_sb = (long)seq_len * d.C; a.fo_st = d.C;
+    a.hstate = w.hstate; a.cstate = w.cstate; a.logdet_out = logdet_out;
+    LFI_TRY(core::launch_inv(a, st));
+  }
+  return LFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// single frame, single step (module API)
+size_t lfi_flowstep_ws_bytes(const lfi_shape *s, int B) {
+  Dims d;
+  if (make_dims(s, &d) != LFI_OK || B < 1) return 0;
+  Bump b(nullptr, 0);
+  b.take<float>((size_t)B * d.D);
+  b.take<float>((size_t)B * d.GH);
+  b.take<float>((size_t)B * d.C * 2);
+  b.take<float>((size_t)B);
+  return round_up_sz(b.off, 256) + lfi_gemm_ws_bytes();
+}
+
+int lfi_flowstep(const lfi_shape *s, const void *derived, const lfi_params *p, int k, int reverse, const float *x,
+                 const float *cond, const float *h_in, const float *c_in, float *h_out, float *c_out, float *y,
+                 float *logdet, float *scale_out, int B, void *ws, size_t ws_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d;
+  LFI_TRY(make_dims(s, &d));
+  LFI_REQUIRE(derived && p && x && cond && h_out && y && logdet && ws, LFI_ERR_ARG, "lfi_flowstep: null argument");
+  LFI_REQUIRE(k >= 0 && k < d.K && B >= 1, LFI_ERR_ARG, "lfi_flowstep: bad step %d / batch %d", k, B);
+  LFI_REQUIRE(d.G == 3 || c_out, LFI_ERR_ARG, "lfi_flowstep: LSTM needs c_out");
+  LFI_REQUIRE(ws_bytes >= lfi_flowstep_ws_bytes(s, B), LFI_ERR_WORKSPACE, "flowstep workspace too small");
+  Bump b(ws, ws_bytes);
+  float *Cact = b.take<float>((size_t)B * d.D);
+  float *G = b.take<float>((size_t)B * d.GH);
+  float *xin = b.take<float>((size_t)B * d.C * 2);
+  float *ldtmp = b.take<float>((size_t)B);
+  void *gws = (char *)ws + round_up_sz(b.off, 256);
+  const size_t gws_bytes = ws_bytes - round_up_sz(b.off, 256);
+  const int In = d.Ci + d.D;
+  // cond_transform with the raw (unfolded) feature vector, then the c-part of gate-ih
+  GemmArgs g1 = gemm_args(0, 1, B, d.D, d.F, cond, d.F, p->wc + (size_t)k * d.D * d.F, d.F, Cact, d.D, LFI_EPI_BIAS | LFI_EPI_LRELU,
+                          p->bc + (size_t)k * d.D);
+  LFI_TRY(gemm_dispatch(LFI_GEMM_FP32, g1, gws, gws_bytes, st));
+  GemmArgs g2 = gemm_args(0, 1, B, d.GH, d.D, Cact, d.D, p->w_ih + (size_t)k * d.GH * In + d.Ci, In, G, d.GH, LFI_EPI_BIAS,
+                          p->b_ih + (size_t)k * d.GH);
+  LFI_TRY(gemm_dispatch(LFI_GEMM_FP32, g2, gws, gws_bytes, st));
+  const size_t koffH = (size_t)k * B * d.H;
+  if (!reverse) {
+    core::FwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.d = d; a.dv = make_view(d, derived, p); a.B = B; a.Tp = 1; a.k_first = k; a.k_last = k;
+    a.x0 = x; a.x_sb = d.C; a.x_st = 0; a.G = G; a.g_ld = d.GH; a.g_k0 = k;
+    a.h0 = h_in ? h_in - koffH : nullptr; a.c0 = c_in ? c_in - koffH : nullptr;
+    a.xin = xin - (size_t)k * B * d.C;  // never touched for a single step, kept valid anyway
+    a.st_h = h_out - koffH; a.st_c = c_out ? c_out - koffH : nullptr;
+    a.ld = logdet; a.ld_accumulate = 1; a.nll = nullptr; a.z_out = y;
+    a.scale_out = scale_out ? scale_out - (size_t)k * B * d.Cz : nullptr;
+    return core::launch_fwd(a, st);
+  }
+  // reverse: state is read and written in place by the persistent kernel
+  if (h_in) LFI_CUDA(cudaMemcpyAsync(h_out, h_in, (size_t)B * d.H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  else LFI_CUDA(cudaMemsetAsync(h_out, 0, (size_t)B * d.H * sizeof(float), st));
+  if (d.G == 4) {
+    if (c_in) LFI_CUDA(cudaMemcpyAsync(c_out, c_in, (size_t)B * d.H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else LFI_CUDA(cudaMemsetAsync(c_out, 0, (size_t)B * d.H * sizeof(float), st));
+  }
+  core::InvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = d; a.dv = make_view(d, derived, p); a.B = B; a.Tc = 1; a.k_hi = k; a.k_lo = k; a.g_k0 = k;
+  a.t_abs0 = 0; a.t_rel0 = 0; a.noise = x; a.G = G; a.g_ld = d.GH;
+  a.faces_out = y; a.fo_sb = d.C; a.fo_st = 0;
+  a.hstate = h_out - koffH; a.cstate = c_out ? c_out - koffH : nullptr;
+  a.logdet_out = ldtmp;
+  LFI_TRY(core::launch_inv(a, st));
+  // logdet += (-sum log s) computed by the kernel
+  LFI_TRY(aux::colsum(logdet, ldtmp, B, 1, B, 1.0f, st));
+  return LFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t lfi_invconv_ws_bytes(int K, int C) {
+  const size_t n = (size_t)K * C * C;
+  return 6 * round_up_sz(n * sizeof(float), 256) + round_up_sz(2 * n * sizeof(double), 256) + 256;
+}
+
+int lfi_invconv_compose(int K, int C, const float *pm, const float *l, const float *u, const float *log_s, const float *sign_s,
+                        float *w, float *winv, void *ws, size_t ws_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  LFI_REQUIRE(pm && l && u && log_s && sign_s && w && ws, LFI_ERR_ARG, "lfi_invconv_compose: null argument");
+  LFI_REQUIRE(C >= 1 && C <= 256 && K >= 1, LFI_ERR_SHAPE, "lfi_invconv_compose: C=%d K=%d", C, K);
+  LFI_REQUIRE(ws_bytes >= lfi_invconv_ws_bytes(K, C), LFI_ERR_WORKSPACE, "invconv workspace too small");
+  Bump b(ws, ws_bytes);
+  const size_t n = (size_t)K * C * C;
+  float *Lm = b.take<float>(n), *Um = b.take<float>(n), *T1 = b.take<float>(n), *Li = b.take<float>(n), *Ui = b.take<float>(n);
+  double *scr = b.take<double>(2 * n);
+  const long sM = (long)C * C;
+  LFI_TRY(aux::lu_build(Lm, Um, l, u, log_s, sign_s, K, C, st));
+  GemmArgs g = gemm_args(0, 0, C, C, C, Lm, C, Um, C, T1, C, 0);
+  g.batch = K; g.sA = sM; g.sB = sM; g.sC = sM;
+  LFI_TRY(gemm_simt(g, st));                                   // L U
+  GemmArgs h = gemm_args(0, 0, C, C, C, pm, C, T1, C, w, C, 0);
+  h.batch = K; h.sA = sM; h.sB = sM; h.sC = sM;
+  LFI_TRY(gemm_simt(h, st));                                   // W = P (L U)
+  if (winv) {
+    LFI_TRY(aux::tri_inverse_f64(Li, Ui, scr, Lm, Um, K, C, st));
+    GemmArgs q = gemm_args(0, 1, C, C, C, Li, C, pm, C, T1, C, 0);  // L^-1 P^-1,  P^-1 = P^T for a permutation
+    q.batch = K; q.sA = sM; q.sB = sM; q.sC = sM;
+    LFI_TRY(gemm_simt(q, st));
+    GemmArgs r = gemm_args(0, 0, C, C, C, Ui, C, T1, C, winv, C, 0);  // U^-1 (L^-1 P^-1)
+    r.batch = K; r.sA = sM; r.sB = sM; r.sC = sM;
+    LFI_TRY(gemm_simt(r, st));
+  }
+  return LFI_OK;
+}
+
+int lfi_invconv_compose_bwd(int K, int C, const float *pm, const float *l, const float *u, const float *log_s,
+                            const float *sign_s, const float *dw, float *dl, float *du, float *dlog_s, void *ws,
+                            size_t ws_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  LFI_REQUIRE(pm && l && u && log_s && sign_s && dw && dl && du && dlog_s && ws, LFI_ERR_ARG, "lfi_invconv_compose_bwd: null argument");
+  LFI_REQUIRE(ws_bytes >= lfi_invconv_ws_bytes(K, C), LFI_ERR_WORKSPACE, "invconv workspace too small");
+  Bump b(ws, ws_bytes);
+  const size_t n = (size_t)K * C * C;
+  float *Lm = b.take<float>(n), *Um = b.take<float>(n), *T1 = b.take<float>(n), *dL = b.take<float>(n), *dU = b.take<float>(n);
+  const long sM = (long)C * C;
+  LFI_TRY(aux::lu_build(Lm, Um, l, u, log_s, sign_s, K, C, st));
+  GemmArgs g = gemm_args(1, 0, C, C, C, pm, C, dw, C, T1, C, 0);   // T1 = P^T dW
+  g.batch = K; g.sA = sM; g.sB = sM; g.sC = sM;
+  LFI_TRY(gemm_simt(g, st));
+  GemmArgs h = gemm_args(0, 1, C, C, C, T1, C, Um, C, dL, C, 0);   // dL = T1 U^T
+  h.batch = K; h.sA = sM; h.sB = sM; h.sC = sM;
+  LFI_TRY(gemm_simt(h, st));
+  GemmArgs q = gemm_args(1, 0, C, C, C, Lm, C, T1, C, dU, C, 0);   // dU = L^T T1
+  q.batch = K; q.sA = sM; q.sB = sM; q.sC = sM;
+  LFI_TRY(gemm_simt(q, st));
+  return aux::lu_mask_grads(dl, du, dlog_s, dL, dU, log_s, sign_s, K, C, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+int lfi_actnorm(const float *x, const float *bias, const float *logs, float *y, int B, int C, int reverse, void *stream) {
+  LFI_REQUIRE(x && bias && logs && y && B >= 1 && C >= 1, LFI_ERR_ARG, "lfi_actnorm: bad argument");
+  return aux::actnorm(x, bias, logs, y, B, C, reverse, (cudaStream_t)stream);
+}
+
+int lfi_matmul(const float *a, const float *bm, const float *bias, float *c, int M, int N, int Kd, int transB, void *stream) {
+  LFI_REQUIRE(a && bm && c, LFI_ERR_ARG, "lfi_matmul: null argument");
+  GemmArgs g = gemm_args(0, transB ? 1 : 0, M, N, Kd, a, Kd, bm, transB ? Kd : N, c, N, bias ? LFI_EPI_BIAS : 0, bias);
+  return gemm_simt(g, (cudaStream_t)stream);
+}
+
+int lfi_nll(const float *z, const float *logdet, float *nll, int B, int C, void *stream) {
+  LFI_REQUIRE(z && logdet && nll && B >= 1 && C >= 1, LFI_ERR_ARG, "lfi_nll: bad argument");
+  return aux::nll(z, logdet, nll, B, C, (cudaStream_t)stream);
+}
+
+int lfi_clip_adam(float *theta, float *grad, float *m, float *v, size_t n, float lr, float beta1, float beta2, float eps,
+                  float max_norm, float grad_scale, int step, float *norm_scratch, void *stream) {
+  LFI_REQUIRE(theta && grad && m && v && norm_scratch && step >= 1, LFI_ERR_ARG, "lfi_clip_adam: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  LFI_TRY(aux::sumsq(norm_scratch, grad, n, st));
+  return aux::clip_adam(theta, grad, m, v, n, lr, beta1, beta2, eps, max_norm, grad_scale, step, norm_scratch, st);
+}
+
+int lfi_gemm(int mode, int transA, int transB, int M, int N, int Kd, const float *A, int lda, long strideA, const float *Bm,
+             int ldb, long strideB, float *Cm, int ldc, long strideC, const float *bias, long strideBias, const float *auxm,
+             int ldaux, long strideAux, int batch, int epi, void *ws, size_t ws_bytes, void *stream) {
+  GemmArgs g = gemm_args(transA, transB, M, N, Kd, A, lda, Bm, ldb, Cm, ldc, epi, bias);
+  g.sA = strideA; g.sB = strideB; g.sC = strideC; g.sBias = strideBias; g.aux = auxm; g.ldaux = ldaux; g.sAux = strideAux;
+  g.batch = batch;
+  return gemm_dispatch(mode, g, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

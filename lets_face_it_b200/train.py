@@ -1,0 +1,90 @@
+"""Fused training step over the flat parameter buffer, with batch-sharded data parallelism.
+
+Semantics of the reference's step (LetsFaceItGlow.training_step + configure_optimizers,
+lets_face_it_glow.py:39-72, final_model.yaml: Adam lr 1e-5 betas (0.9, 0.9999), gradient_clip_val 20):
+loss = mean_t mean_b NLL bits; backward; clip_grad_norm_(20); Adam.  Here the whole step is a handful of
+stream-ordered launches with no host synchronisation: forward + backward through the C ABI, one NCCL
+all-reduce of the flat fp32 gradient when world_size > 1 (the only exchange the path has),
+and a fused clip+Adam over the flat buffer.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _cabi as cabi
+
+LN2 = math.log(2.0)
+
+
+class Trainer:
+    def __init__(self, model, lr=None, betas=None, eps=None, max_norm=None, process_group=None, dropout=True):
+        hp = model.hparams
+        self.model = model
+        self.eng = model.engine()
+        adam = hp.Optim["args"]["adam"]
+        self.lr = float(lr if lr is not None else hp.lr)
+        self.betas = tuple(betas if betas is not None else adam["betas"])
+        self.eps = float(eps if eps is not None else adam["eps"])
+        self.max_norm = float(max_norm if max_norm is not None else (hp.gradient_clip_val or 0))
+        self.dropout = dropout
+        dev = self.eng.theta.device
+        n = self.eng.n_theta
+        self.m = torch.zeros(n, device=dev)
+        self.v = torch.zeros(n, device=dev)
+        self.gflat = self.eng.new_flat_grad()
+        self.scratch = torch.zeros(2, device=dev)
+        self.step_count = 0
+        self.pg = process_group
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
+        self._dnll = {}
+
+    def broadcast_parameters(self, src=0):
+        """Replicas start identical (and share the ActNorm data-dependent init of rank `src`)."""
+        if self.world > 1:
+            torch.distributed.broadcast(self.eng.theta, src, group=self.pg)
+
+    def step(self, batch, masks=None):
+        """One optimizer step on this rank's shard of sequences.  Returns the (device) loss of the shard."""
+        eng, model = self.eng, self.model
+        x0 = batch["p1_face"]
+        B, T = x0.shape[0], x0.shape[1]
+        Tp = T - eng.start_ts
+        if masks is None and self.dropout and model.training:
+            masks = model._masks(Tp, B, eng.theta.device)
+        if model.training and not all(l.actnorm.inited for l in model.glow.flow.layers):
+            model._ddi(eng, batch, masks)
+        z, nll = eng.train_forward(batch, masks)
+        key = (Tp, B)
+        if key not in self._dnll:
+            self._dnll[key] = torch.full((Tp, B), 1.0 / (Tp * B), device=eng.theta.device)
+        self.gflat.zero_()
+        eng.train_backward(z, self._dnll[key], self.gflat)
+        g = self.gflat[:eng.n_theta]
+        if self.world > 1:
+            torch.distributed.all_reduce(g, group=self.pg)  # sum; averaged by grad_scale below
+        self.step_count += 1
+        cabi.check(cabi.lib().lfi_clip_adam(eng.theta.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), eng.n_theta,
+                                            self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0 / self.world,
+                                            self.step_count, self.scratch.data_ptr(), cabi.stream_ptr()), "lfi_clip_adam")
+        return nll.mean() - eng.logdet_const() / LN2
+
+    def grad_norm(self):
+        """Global gradient norm of the last step (after the all-reduce average, before clipping)."""
+        return torch.sqrt(self.scratch[0]) / self.world
+
+
+def shard_batch(batch, rank, world):
+    """Contiguous, equal shards of the sequence batch; B must divide evenly so the mean over
+    the global batch equals the mean of the per-rank means."""
+    out = {}
+    for k, v in batch.items():
+        B = v.shape[0]
+        if B % world:
+            raise ValueError("batch size %d is not divisible by world size %d" % (B, world))
+        n = B // world
+        out[k] = v[rank * n:(rank + 1) * n]
+    return out
