@@ -92,7 +92,7 @@ inline int make_dims(const lfi_shape *s, Dims *d) {
     d->enc_off[m] = F; d->enc_offe[m] = Fe; d->enc_w[m] = 0; d->enc_we[m] = 0;
     if (s->hist[m] <= 0) continue;
     LFI_REQUIRE(s->dim[m] >= 1, LFI_ERR_SHAPE, "modality %d: dim must be >= 1", m);
-    LFI_REQUIRE(s->ehid[m] >= 0 && s->ehid[m] % 4 == 0, LFI_ERR_SHAPE, "modality %d: encoder hidden must be a multiple of 4", m);
+    LFI_REQUIRE(s->ehid[m] >= 0, LFI_ERR_SHAPE, "modality %d: encoder hidden must be >= 0", m);
     if (m == 0) LFI_REQUIRE(s->ehid[0] == 0 && s->dim[0] == s->C, LFI_ERR_SHAPE, "p1_face must be 'enc: none' with dim == C");
     if (s->hist[m] > st) st = s->hist[m];
     if (s->ehid[m] > 0) { d->enc_w[m] = 2 * s->ehid[m]; d->enc_we[m] = s->ehid[m]; }

@@ -85,6 +85,8 @@ class Engine:
                 info = feature_encoder.modality_info(m)
                 sh.hist[i], sh.dim[i], sh.ehid[i] = info
             L = cabi.lib()
+            if L.lfi_feature_dim(ctypes.byref(sh)) < 0:
+                raise RuntimeError("unsupported shape: %s" % L.lfi_last_error().decode())
             if L.lfi_feature_dim(ctypes.byref(sh)) != self.F:
                 raise RuntimeError("feature encoder dim %d != cond_transform input %d (use_frame_nb / lstm / mlp / cnn encoders are "
                                    "outside the accelerated path, SURVEY.md §2 row 5)" % (L.lfi_feature_dim(ctypes.byref(sh)), self.F))
