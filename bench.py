@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sample", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="profiling helper: warm up, then run ONE step between cudaProfilerStart/Stop and exit "
+                         "(use with ncu --profile-from-start off); prints no bench line")
     return ap.parse_args()
 
 
@@ -229,6 +232,13 @@ def run_ours(a):
     # ---- device-resident throughput --------------------------------------------------------------------------
     for _ in range(max(a.warmup, 3)):
         trainer.step(dbatch)
+    if a.ncu_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        trainer.step(dbatch)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     clocks = ClockSampler(local)
     clocks.start()
     n0 = L.lfi_launch_count()
