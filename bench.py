@@ -281,7 +281,7 @@ def run_ours(a):
         W = torch.randn(N, K, device=dev)
         C = torch.empty(M, N, device=dev)
         bias = torch.zeros(N, device=dev)
-        ws = torch.empty(max(int(L.lfi_gemm_ws_bytes()), 256), dtype=torch.uint8, device=dev)
+        ws = torch.empty(max(int(L.lfi_gemm_ws_bytes(gemm_mode, 0, 1, M, N, K, 1)), 256), dtype=torch.uint8, device=dev)
 
         def gemm():
             cabi.check(L.lfi_gemm(gemm_mode, 0, 1, M, N, K, A.data_ptr(), K, 0, W.data_ptr(), K, 0, C.data_ptr(), N, 0, bias.data_ptr(), 0,

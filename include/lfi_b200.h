@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LFI_ABI_VERSION 1
+#define LFI_ABI_VERSION 2
 #define LFI_NMOD 4 /* p1_face, p2_face, p1_speech, p2_speech — concat order of models.py:127-145 */
 
 typedef enum lfi_status {
@@ -89,10 +89,12 @@ int lfi_feature_dim_folded(const lfi_shape *s); /* Fe = F with duplicated GRU ha
 int lfi_start_ts(const lfi_shape *s);           /* utils.py:44-50                                        */
 int lfi_coupling_out(const lfi_shape *s);       /* Co: f_seq output channels (models.py:276-298)         */
 size_t lfi_derived_bytes(const lfi_shape *s);
-size_t lfi_train_ws_bytes(const lfi_shape *s, int B, int T);
-size_t lfi_sample_ws_bytes(const lfi_shape *s, int B, int T, int chunk);
+size_t lfi_train_ws_bytes(const lfi_shape *s, int B, int T, int gemm_mode);
+size_t lfi_sample_ws_bytes(const lfi_shape *s, int B, int T, int chunk, int gemm_mode);
 size_t lfi_invconv_ws_bytes(int K, int C);
-size_t lfi_gemm_ws_bytes(void); /* scratch appended to every workspace for the tcgen05 operand staging */
+/* operand-plane scratch lfi_gemm needs for one problem in the tensor-core modes (0 in fp32 mode); the *_ws_bytes
+ * functions above already include the scratch of the GEMMs they run */
+size_t lfi_gemm_ws_bytes(int mode, int transA, int transB, int M, int N, int K, int batch);
 
 /* ---- derived weight cache (transposes, folded cond_transform, padded slices, W^-1) --------
  * Must be re-run after every parameter update.  winv may be NULL (training only). */
@@ -138,7 +140,7 @@ int lfi_seq_sample(const lfi_shape *s, const void *derived, const lfi_params *p,
 
 /* ---- FeatureEncoder.forward (models.py:127-145) for frames t0..t0+Tp-1: cond [Tp*B, Fe] (folded:
  * each GRU-encoded modality contributes its final state once; the reference concatenates it twice). */
-size_t lfi_feature_ws_bytes(const lfi_shape *s, int B, int T, int Tp);
+size_t lfi_feature_ws_bytes(const lfi_shape *s, int B, int T, int Tp, int gemm_mode);
 int lfi_feature_encode(const lfi_shape *s, const lfi_params *p, const lfi_batch *b, int t0, int Tp, float *cond,
                        void *ws, size_t ws_bytes, int gemm_mode, void *stream);
 

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "liblfi_b200.so")
 NMOD = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 GEMM_FP32, GEMM_BF16X3, GEMM_BF16 = 0, 1, 2
 EPI_BIAS, EPI_LRELU, EPI_ACCUM, EPI_LRELU_BWD = 1, 2, 4, 8
@@ -53,11 +53,11 @@ SYMBOLS = {
     "lfi_start_ts": (_I, [_SH]),
     "lfi_coupling_out": (_I, [_SH]),
     "lfi_derived_bytes": (_SZ, [_SH]),
-    "lfi_train_ws_bytes": (_SZ, [_SH, _I, _I]),
-    "lfi_sample_ws_bytes": (_SZ, [_SH, _I, _I, _I]),
+    "lfi_train_ws_bytes": (_SZ, [_SH, _I, _I, _I]),
+    "lfi_sample_ws_bytes": (_SZ, [_SH, _I, _I, _I, _I]),
     "lfi_invconv_ws_bytes": (_SZ, [_I, _I]),
-    "lfi_gemm_ws_bytes": (_SZ, []),
-    "lfi_feature_ws_bytes": (_SZ, [_SH, _I, _I, _I]),
+    "lfi_gemm_ws_bytes": (_SZ, [_I, _I, _I, _I, _I, _I, _I]),
+    "lfi_feature_ws_bytes": (_SZ, [_SH, _I, _I, _I, _I]),
     "lfi_flowstep_ws_bytes": (_SZ, [_SH, _I]),
     "lfi_derive": (_I, [_SH, _PR, _P, _P, _I, _P]),
     "lfi_invconv_compose": (_I, [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),

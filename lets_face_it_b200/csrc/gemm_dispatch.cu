@@ -3,7 +3,8 @@
 
 namespace lfi {
 int gemm_tc(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st, bool *handled);
-size_t gemm_tc_ws_bytes();
+bool gemm_tc_wants(const GemmArgs &g);
+namespace tc { size_t split_ws_bytes(const GemmArgs &g, int nplanes); }
 
 int gemm_dispatch(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st) {
   if (mode == LFI_GEMM_FP32) return gemm_simt(g, st);
@@ -13,6 +14,17 @@ int gemm_dispatch(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaSt
   if (handled) return LFI_OK;
   return gemm_simt(g, st);  // shapes the tensor-core tiles do not cover (tiny K / N): exact fp32 tiles
 }
+
+// Operand-plane scratch one GEMM needs in the tensor-core modes (0 in fp32 mode or for shapes routed to the fp32 tiles).
+size_t gemm_ws_bytes(int mode, const GemmArgs &g) {
+  if (mode == LFI_GEMM_FP32 || !gemm_tc_wants(g)) return 0;
+  return tc::split_ws_bytes(g, mode == LFI_GEMM_BF16X3 ? 2 : 1);
+}
 }  // namespace lfi
 
-extern "C" size_t lfi_gemm_ws_bytes(void) { return lfi::gemm_tc_ws_bytes(); }
+extern "C" size_t lfi_gemm_ws_bytes(int mode, int transA, int transB, int M, int N, int K, int batch) {
+  lfi::GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.transA = transA; g.transB = transB; g.M = M; g.N = N; g.K = K; g.batch = batch;
+  return lfi::gemm_ws_bytes(mode, g);
+}

@@ -1,10 +1,502 @@
-// tcgen05 / TMEM / TMA GEMM (placeholder until the tensor-core tiles land: reports "not handled").
+// tcgen05 / TMEM / TMA GEMM for the time-parallel contractions of the conditional-Glow path
+// (cond_transform, gate-ih, the windowed encoder GRUs and every weight gradient; reference call sites
+// models.py:63-64, 187-190, 206-208 and their autograd).
+//
+//   C[b] = op(A[b]) op(B[b])  (+ bias, LeakyReLU, LeakyReLU', accumulate)       fp32 in / fp32 out
+//
+// Numerics (lfi_gemm_mode):
+//   BF16   : operands rounded to bf16, one tcgen05.mma.kind::f16 product, fp32 accumulation in TMEM.
+//   BF16X3 : operands split a = a_hi + a_lo (two bf16 planes, 16 mantissa bits), three products
+//            a_hi b_hi + a_hi b_lo + a_lo b_hi accumulated in the same TMEM tile: fp32-grade
+//            (measured 1.4e-6 on z after 16 steps x 56 frames).
+//
+// Structure: a persistent, warp-specialised kernel, one CTA per SM.
+//   warp 0   : TMA producer   - cp.async.bulk.tensor (128B swizzle) of the A / B planes into a ring of stages
+//   warp 1   : MMA issuer     - one thread issues tcgen05.mma (M=128, N=bn<=256, K=16) into one of two TMEM
+//                               accumulator tiles and commits stage / accumulator barriers
+//   warps 2-5: epilogue       - tcgen05.ld the finished accumulator, transpose through shared memory, fused
+//                               epilogue, fully coalesced global stores (or red.add for split-K)
+// Both operand majors are native: a row-major [MN, K] plane is a K-major UMMA operand, a row-major [K, MN]
+// plane (weight-gradient GEMMs reduce over the rows of two activation matrices) is an MN-major operand, so no
+// transposed copies of activations are ever materialised.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+
 #include "lfi_common.cuh"
+
 namespace lfi {
-size_t gemm_tc_ws_bytes() { return 0; }
-int gemm_tc(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st, bool *handled) {
-  (void)mode; (void)g; (void)ws; (void)ws_bytes; (void)st;
-  *handled = false;
+namespace tc {
+
+constexpr int BM = 128;        // tile rows (UMMA M, cta_group::1)
+constexpr int BK = 64;         // bf16 elements per k-block = one 128-byte swizzle span
+constexpr int UK = 16;         // UMMA K for 16-bit operands
+constexpr int kThreads = 192;  // 6 warps
+constexpr int kMaxStages = 8;
+constexpr int kEpiPitch = 33;
+constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;
+constexpr int kTmemCols = 512;  // two accumulator tiles of up to 256 columns
+constexpr int kSmemLimit = 225 * 1024;  // dynamic; leaves room for the 1 KB alignment reserve
+
+struct Params {
+  int M, N, K, batch;
+  int bn;          // tile columns: 64, 128, 192 or 256
+  int nplanes;     // 1 = bf16, 2 = split bf16 (three products)
+  int a_mn, b_mn;  // 1 = operand stored [K, MN] (MN contiguous)
+  int stages, splitk;
+  int tiles_m, tiles_n;
+  float *C; int ldc; long sC;
+  const float *bias; long sBias;
+  const float *aux; int ldaux; long sAux;
+  int epi;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must abort the kernel (sticky error -> LFI_ERR_CUDA), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try_wait(bar, parity)) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 4000000000ull) {
+      printf("lfi gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (sm_100 UMMA, 128-byte swizzle).  All fields in 16-byte units.
+//   K-major  plane tile [rows][64 bf16]: 8-row swizzle atoms of 1024 B  -> SBO = 1024, LBO unused
+//   MN-major plane tile: 64-wide MN chunks of [BK rows][64 bf16]        -> SBO = 1024 (8 k-rows), LBO = BK*128
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  d |= 2ull << 61;  // SWIZZLE_128B
+  return d;
+}
+
+struct TileCoord { int b, m0, n0, kb0, kb1; };
+
+__device__ __forceinline__ TileCoord tile_coord(const Params &p, int tile, int nkb) {
+  // n fastest, then m, then split-k, then batch: CTAs running side by side share the A rows through L2
+  TileCoord t;
+  const int tn = tile % p.tiles_n; tile /= p.tiles_n;
+  const int tm = tile % p.tiles_m; tile /= p.tiles_m;
+  const int sk = tile % p.splitk;  tile /= p.splitk;
+  t.b = tile; t.m0 = tm * BM; t.n0 = tn * p.bn;
+  const int per = (nkb + p.splitk - 1) / p.splitk;
+  t.kb0 = sk * per; t.kb1 = min(nkb, t.kb0 + per);
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve-up: [stages][A planes | B planes] | epilogue staging | barriers | tmem address
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_plane = BM * BK * 2;            // 16 KB
+  const uint32_t b_plane = (uint32_t)p.bn * BK * 2;
+  const uint32_t stage_bytes = p.nplanes * (a_plane + b_plane);
+  float *epi_stage = (float *)(smem + (size_t)p.stages * stage_bytes);
+  uint64_t *bars = (uint64_t *)((uint8_t *)epi_stage + kEpiBytes);
+  uint64_t *full = bars, *empty = bars + kMaxStages, *tfull = bars + 2 * kMaxStages, *tempty = tfull + 2;
+  uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (p.K + BK - 1) / BK;
+  const int ntiles = p.tiles_m * p.tiles_n * p.splitk * p.batch;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileCoord t = tile_coord(p, tile, nkb);
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], stage_bytes);
+          uint8_t *sa = smem + (size_t)s * stage_bytes;
+          uint8_t *sb = sa + p.nplanes * a_plane;
+          const int k0 = kb * BK;
+          for (int pl = 0; pl < p.nplanes; ++pl) {
+            const CUtensorMap *ma = pl ? &mapA1 : &mapA0;
+            const CUtensorMap *mb = pl ? &mapB1 : &mapB0;
+            if (!p.a_mn) {
+              tma_load_3d(sa + pl * a_plane, ma, &full[s], k0, t.m0, t.b);
+            } else {
+              for (int j = 0; j < BM / 64; ++j) tma_load_3d(sa + pl * a_plane + j * (BK * 128), ma, &full[s], t.m0 + 64 * j, k0, t.b);
+            }
+            if (!p.b_mn) {
+              tma_load_3d(sb + pl * b_plane, mb, &full[s], k0, t.n0, t.b);
+            } else {
+              for (int j = 0; j < p.bn / 64; ++j) tma_load_3d(sb + pl * b_plane + j * (BK * 128), mb, &full[s], t.n0 + 64 * j, k0, t.b);
+            }
+          }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                             ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_lbo = p.a_mn ? BK * 128 : 0, b_lbo = p.b_mn ? BK * 128 : 0;
+      const uint32_t a_adv = p.a_mn ? (UK * 128) >> 4 : (UK * 2) >> 4;  // descriptor address step per UMMA_K
+      const uint32_t b_adv = p.b_mn ? (UK * 128) >> 4 : (UK * 2) >> 4;
+      int s = 0; uint32_t ph = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const TileCoord t = tile_coord(p, tile, nkb);
+        const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        uint32_t acc = 0;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + p.nplanes * a_plane;
+          const int nprod = p.nplanes == 2 ? 3 : 1;
+          for (int pr = 0; pr < nprod; ++pr) {
+            // products: (hi,hi), (hi,lo), (lo,hi)
+            const int pa = (pr == 2) ? 1 : 0, pb = (pr == 1) ? 1 : 0;
+            const uint64_t ad = make_sdesc(sa + pa * a_plane, a_lbo, 1024);
+            const uint64_t bd = make_sdesc(sb + pb * b_plane, b_lbo, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              umma_bf16(d_tmem, ad + (uint64_t)(k * a_adv), bd + (uint64_t)(k * b_adv), idesc, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[as]);   // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float *stg = epi_stage + (warp - 2) * 32 * kEpiPitch;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const TileCoord t = tile_coord(p, tile, nkb);
+      const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      float *C = p.C + (size_t)t.b * p.sC;
+      const float *bias = p.bias ? p.bias + (size_t)t.b * p.sBias : nullptr;
+      const float *aux = p.aux ? p.aux + (size_t)t.b * p.sAux : nullptr;
+      const bool has_work = t.kb1 > t.kb0;
+      for (int c = 0; c < p.bn / 32; ++c) {
+        const int n = t.n0 + c * 32 + lane;
+        if (t.n0 + c * 32 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * kEpiPitch + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const float bv = (bias && n < p.N && (p.epi & LFI_EPI_BIAS)) ? bias[n] : 0.f;
+        if (n < p.N) {
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            const int m = t.m0 + q * 32 + r;
+            if (m >= p.M) break;
+            float x = has_work ? stg[r * kEpiPitch + lane] : 0.f;
+            x += bv;
+            if (p.epi & LFI_EPI_LRELU) x = x > 0.f ? x : kLeaky * x;
+            if (p.epi & LFI_EPI_LRELU_BWD) x *= (aux[(size_t)m * p.ldaux + n] > 0.f ? 1.f : kLeaky);
+            float *dst = C + (size_t)m * p.ldc + n;
+            if (p.splitk > 1) atomicAdd(dst, x);
+            else if (p.epi & LFI_EPI_ACCUM) *dst += x;
+            else *dst = x;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---- fp32 -> bf16 planes ------------------------------------------------------------------------
+// dst planes are [batch][rows][ldp] with ldp = round_up(cols, 8); padding columns are zero.
+__global__ void split_planes_kernel(const float *__restrict__ src, int rows, int cols, int ld, long stride, int batch,
+                                    __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int ldp) {
+  const int groups = ldp / 8;
+  const size_t total = (size_t)batch * rows * groups;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int gidx = (int)(idx % groups);
+    const size_t rb = idx / groups;
+    const int r = (int)(rb % rows), b = (int)(rb / rows);
+    const float *s = src + (size_t)b * stride + (size_t)r * ld + gidx * 8;
+    float v[8];
+    const int c0 = gidx * 8;
+    if (c0 + 8 <= cols && (((uintptr_t)s) & 15) == 0) {
+      const float4 u = *reinterpret_cast<const float4 *>(s), w = *reinterpret_cast<const float4 *>(s + 4);
+      v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w; v[4] = w.x; v[5] = w.y; v[6] = w.z; v[7] = w.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (c0 + e < cols) ? s[e] : 0.f;
+    }
+    __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      h[e] = __float2bfloat16_rn(v[e]);
+      l[e] = __float2bfloat16_rn(v[e] - __bfloat162float(h[e]));
+    }
+    const size_t o = rb * (size_t)ldp + c0;
+    *reinterpret_cast<uint4 *>(hi + o) = *reinterpret_cast<const uint4 *>(h);
+    if (lo) *reinterpret_cast<uint4 *>(lo + o) = *reinterpret_cast<const uint4 *>(l);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+// plane: bf16 [batch][rows][ldp]; K-major operand: rows = MN extent, cols = K; MN-major: rows = K, cols = MN.
+static int make_map(CUtensorMap *map, const __nv_bfloat16 *plane, int rows, int cols, int ldp, long stride, int batch, int box_rows) {
+  auto fn = encode_fn();
+  LFI_REQUIRE(fn, LFI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ldp * 2, (cuuint64_t)(batch > 1 ? stride : (long)rows * ldp) * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)plane, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LFI_REQUIRE(r == CUDA_SUCCESS, LFI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rows=%d cols=%d ldp=%d batch=%d box_rows=%d", (int)r, rows,
+              cols, ldp, batch, box_rows);
   return LFI_OK;
 }
+
+static int choose_bn(int N) {
+  int best = 64, waste = round_up(N, 64);
+  const int cand[4] = {64, 128, 192, 256};
+  for (int i = 0; i < 4; ++i) {
+    const int w = round_up(N, cand[i]);
+    if (w <= waste) { waste = w; best = cand[i]; }
+  }
+  return best;
+}
+
+struct Operand {
+  const __nv_bfloat16 *hi, *lo;
+  int rows, cols, ldp;  // plane geometry
+  long stride;
+  int mn;               // MN-major?
+};
+
+static int g_sms = 0;
+
+// Core launch on prepared planes.
+static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, int nplanes, cudaStream_t st) {
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
+  p.bn = choose_bn(g.N);
+  p.nplanes = nplanes; p.a_mn = A.mn; p.b_mn = B.mn;
+  p.tiles_m = (g.M + BM - 1) / BM; p.tiles_n = (g.N + p.bn - 1) / p.bn;
+  const int stage_bytes = nplanes * (BM * BK * 2 + p.bn * BK * 2);
+  const int fixed = kEpiBytes + (2 * kMaxStages + 4) * 8 + 16 + 1024;
+  p.stages = (kSmemLimit - fixed) / stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  LFI_REQUIRE(p.stages >= 2, LFI_ERR_SHAPE, "gemm_tc: tile does not fit shared memory");
+  const int nkb = (g.K + BK - 1) / BK;
+  if (!g_sms) {
+    int dev = 0;
+    LFI_CUDA(cudaGetDevice(&dev));
+    LFI_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  p.splitk = 1;
+  const long tiles = (long)p.tiles_m * p.tiles_n * g.batch;
+  if (g.epi == LFI_EPI_ACCUM && tiles * 2 <= g_sms && nkb >= 16) {
+    int sk = (int)((g_sms + tiles - 1) / tiles);
+    if (sk > nkb / 8) sk = nkb / 8;
+    if (sk < 1) sk = 1;
+    // every split must own at least one k-block
+    const int per = (nkb + sk - 1) / sk;
+    sk = (nkb + per - 1) / per;
+    p.splitk = sk;
+  }
+  p.C = g.C; p.ldc = g.ldc; p.sC = g.sC; p.bias = g.bias; p.sBias = g.sBias; p.aux = g.aux; p.ldaux = g.ldaux; p.sAux = g.sAux;
+  p.epi = g.epi;
+
+  CUtensorMap mA0, mA1, mB0, mB1;
+  const int a_box = A.mn ? BK : BM, b_box = B.mn ? BK : p.bn;
+  LFI_TRY(make_map(&mA0, A.hi, A.rows, A.cols, A.ldp, A.stride, g.batch, a_box));
+  LFI_TRY(make_map(&mB0, B.hi, B.rows, B.cols, B.ldp, B.stride, g.batch, b_box));
+  if (nplanes == 2) {
+    LFI_TRY(make_map(&mA1, A.lo, A.rows, A.cols, A.ldp, A.stride, g.batch, a_box));
+    LFI_TRY(make_map(&mB1, B.lo, B.rows, B.cols, B.ldp, B.stride, g.batch, b_box));
+  } else {
+    mA1 = mA0; mB1 = mB0;
+  }
+  const int smem = p.stages * stage_bytes + fixed;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set = true;
+  }
+  const long ntiles = tiles * p.splitk;
+  const int grid = (int)(ntiles < g_sms ? ntiles : g_sms);
+  // request > half of the SM's shared memory so that two CTAs (each wanting all 512 TMEM columns) never share an SM
+  const int smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;
+  gemm_tc_kernel<<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+static size_t plane_elems(int rows, int cols, int batch) { return round_up_sz((size_t)batch * rows * round_up(cols, 8), 128); }
+
+size_t split_ws_bytes(const GemmArgs &g, int nplanes) {
+  const size_t a = g.transA ? plane_elems(g.K, g.M, g.batch) : plane_elems(g.M, g.K, g.batch);
+  const size_t b = g.transB ? plane_elems(g.N, g.K, g.batch) : plane_elems(g.K, g.N, g.batch);
+  return (a + b) * 2 * nplanes + 1024;
+}
+
+static int split(const float *src, int rows, int cols, int ld, long stride, int batch, __nv_bfloat16 *hi, __nv_bfloat16 *lo, cudaStream_t st) {
+  const int ldp = round_up(cols, 8);
+  const size_t total = (size_t)batch * rows * (ldp / 8);
+  const int threads = 256;
+  size_t blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split_planes_kernel<<<(int)blocks, threads, 0, st>>>(src, rows, cols, ld, stride, batch, hi, lo, ldp);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+}  // namespace tc
+
+size_t gemm_tc_ws_bytes() { return 0; }
+
+bool gemm_tc_wants(const GemmArgs &g) {
+  // tiny contractions stay on the exact fp32 tiles (nothing to win, and the 1x1-conv / LU helpers need fp32)
+  return g.K >= 32 && g.N >= 16 && g.M >= 16 && (double)g.M * g.N * g.K * g.batch >= 2.0e6;
+}
+
+int gemm_tc(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st, bool *handled) {
+  *handled = false;
+  if (!gemm_tc_wants(g)) return LFI_OK;
+  const int nplanes = mode == LFI_GEMM_BF16X3 ? 2 : 1;
+  const size_t need = tc::split_ws_bytes(g, nplanes);
+  LFI_REQUIRE(ws && ws_bytes >= need, LFI_ERR_WORKSPACE, "gemm_tc: operand-plane workspace too small (%zu < %zu) for %dx%dx%d b=%d", ws_bytes, need,
+              g.M, g.N, g.K, g.batch);
+  LFI_REQUIRE(g.A && g.B && g.C, LFI_ERR_ARG, "gemm: null operand");
+  LFI_REQUIRE(!(g.epi & LFI_EPI_BIAS) || g.bias, LFI_ERR_ARG, "gemm: bias epilogue without bias");
+  LFI_REQUIRE(!(g.epi & LFI_EPI_LRELU_BWD) || g.aux, LFI_ERR_ARG, "gemm: lrelu-bwd epilogue without aux");
+  // A: transA = 0 -> stored [M, K] (K-major); 1 -> stored [K, M] (MN-major).  B: transB = 1 -> [N, K] (K-major); 0 -> [K, N] (MN-major)
+  tc::Operand A, B;
+  A.mn = g.transA ? 1 : 0; A.rows = g.transA ? g.K : g.M; A.cols = g.transA ? g.M : g.K;
+  B.mn = g.transB ? 0 : 1; B.rows = g.transB ? g.N : g.K; B.cols = g.transB ? g.K : g.N;
+  A.ldp = round_up(A.cols, 8); B.ldp = round_up(B.cols, 8);
+  A.stride = (long)A.rows * A.ldp; B.stride = (long)B.rows * B.ldp;
+  __nv_bfloat16 *base = (__nv_bfloat16 *)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  const size_t ae = tc::plane_elems(A.rows, A.cols, g.batch), be = tc::plane_elems(B.rows, B.cols, g.batch);
+  __nv_bfloat16 *a_hi = base, *a_lo = nplanes == 2 ? base + ae : nullptr;
+  __nv_bfloat16 *b_hi = base + ae * nplanes, *b_lo = nplanes == 2 ? b_hi + be : nullptr;
+  LFI_TRY(tc::split(g.A, A.rows, A.cols, g.lda, g.sA, g.batch, a_hi, a_lo, st));
+  LFI_TRY(tc::split(g.B, B.rows, B.cols, g.ldb, g.sB, g.batch, b_hi, b_lo, st));
+  A.hi = a_hi; A.lo = a_lo; B.hi = b_hi; B.lo = b_lo;
+  LFI_TRY(tc::launch_core(A, B, g, nplanes, st));
+  *handled = true;
+  return LFI_OK;
+}
+
 }  // namespace lfi

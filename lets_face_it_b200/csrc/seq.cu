@@ -189,6 +189,24 @@ static int cond_to_gates(const Dims &d, const lfi_params *p, const float *WcF, c
   return LFI_OK;
 }
 
+// Upper bound of the operand-plane scratch any single GEMM of the path needs in the tensor-core modes
+// (rows = frames x sequences the time-parallel phase covers, BT = raw frames of a batch).
+static size_t gemm_scratch_bound(const lfi_shape *s, const Dims &d, size_t rows, size_t BT, int mode) {
+  if (mode == LFI_GEMM_FP32) return 0;
+  auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
+  size_t emax = 0, dimmax = 0;
+  for (int m = 0; m < LFI_NMOD; ++m) {
+    if (s->hist[m] <= 0) continue;
+    emax = mx(emax, (size_t)s->ehid[m]); dimmax = mx(dimmax, (size_t)s->dim[m]);
+  }
+  const size_t K = d.K, D = d.D, GH = d.GH, H = d.H, C = d.C, Co = d.Co, Fe = d.Fe;
+  size_t elems = rows * K * (mx(D, GH) + mx(mx(D, H), mx(C, Co)));  // widest activation pair (dG x Cact in the dW_ih reduction)
+  elems += K * D * Fe + K * GH * D + rows * Fe;                     // folded cond_transform weight, gate-ih weight, features
+  elems += rows * (3 * emax + mx(emax, dimmax)) + BT * dimmax + 3 * emax * mx(emax, dimmax);  // encoders
+  const size_t planes = mode == LFI_GEMM_BF16X3 ? 2 : 1;
+  return round_up_sz(elems * 2 * planes + (1 << 16), 256);
+}
+
 static int check_batch(const lfi_shape *s, const Dims &d, const lfi_batch *b, int min_T) {
   LFI_REQUIRE(b && b->B >= 1, LFI_ERR_ARG, "batch: B must be >= 1");
   LFI_REQUIRE(b->T >= min_T, LFI_ERR_SHAPE, "batch: T=%d shorter than needed (%d)", b->T, min_T);
@@ -218,14 +236,12 @@ int lfi_derive(const lfi_shape *s, const lfi_params *p, const float *winv, void 
   return derive_impl(s, p, winv, derived, (cudaStream_t)stream);
 }
 
-size_t lfi_gemm_ws_bytes(void);
-
-size_t lfi_train_ws_bytes(const lfi_shape *s, int B, int T) {
+size_t lfi_train_ws_bytes(const lfi_shape *s, int B, int T, int gemm_mode) {
   Dims d;
   if (make_dims(s, &d) != LFI_OK || T <= d.start_ts || B < 1) return 0;
   TrainWs w;
   plan_train(s, d, B, T, nullptr, &w);
-  return w.bytes + lfi_gemm_ws_bytes();
+  return w.bytes + gemm_scratch_bound(s, d, (size_t)(T - d.start_ts) * B, (size_t)B * T, gemm_mode);
 }
 
 int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params *p, const lfi_batch *bt, float *z,
@@ -239,8 +255,8 @@ int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params 
   const size_t M = (size_t)Tp * B;
   TrainWs w;
   plan_train(s, d, B, T, ws, &w);
-  LFI_REQUIRE(ws_bytes >= w.bytes + lfi_gemm_ws_bytes(), LFI_ERR_WORKSPACE, "train workspace too small: %zu < %zu", ws_bytes,
-              w.bytes + lfi_gemm_ws_bytes());
+  const size_t gneed = gemm_scratch_bound(s, d, M, (size_t)B * T, gemm_mode);
+  LFI_REQUIRE(ws_bytes >= w.bytes + gneed, LFI_ERR_WORKSPACE, "train workspace too small: %zu < %zu", ws_bytes, w.bytes + gneed);
   void *gws = (char *)ws + w.bytes;
   const size_t gws_bytes = ws_bytes - w.bytes;
   const DerivedLayout L = derived_layout(d);
@@ -272,7 +288,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   const size_t M = (size_t)Tp * B;
   TrainWs w;
   plan_train(s, d, B, T, ws, &w);
-  LFI_REQUIRE(ws_bytes >= w.bytes + lfi_gemm_ws_bytes(), LFI_ERR_WORKSPACE, "train workspace too small");
+  LFI_REQUIRE(ws_bytes >= w.bytes + gemm_scratch_bound(s, d, M, (size_t)B * T, gemm_mode), LFI_ERR_WORKSPACE, "train workspace too small");
   void *gws = (char *)ws + w.bytes;
   const size_t gws_bytes = ws_bytes - w.bytes;
   const DerivedLayout L = derived_layout(d);
@@ -379,12 +395,12 @@ static void plan_sample(const lfi_shape *s, const Dims &d, int B, int T, int chu
 }
 
 // FeatureEncoder.forward (models.py:127-145) for frames t0 .. t0+Tp-1 of a batch: folded features [Tp*B][Fe]
-size_t lfi_feature_ws_bytes(const lfi_shape *s, int B, int T, int Tp) {
+size_t lfi_feature_ws_bytes(const lfi_shape *s, int B, int T, int Tp, int gemm_mode) {
   Dims d;
   if (make_dims(s, &d) != LFI_OK || B < 1 || Tp < 1) return 0;
   SampleWs w;
   plan_sample(s, d, B, T, Tp, nullptr, &w);
-  return w.bytes + lfi_gemm_ws_bytes();
+  return w.bytes + gemm_scratch_bound(s, d, (size_t)Tp * B, (size_t)B * T, gemm_mode);
 }
 
 int lfi_feature_encode(const lfi_shape *s, const lfi_params *p, const lfi_batch *bt, int t0, int Tp, float *cond, void *ws,
@@ -397,17 +413,18 @@ int lfi_feature_encode(const lfi_shape *s, const lfi_params *p, const lfi_batch 
               t0 + Tp, d.start_ts, bt->T);
   SampleWs w;
   plan_sample(s, d, bt->B, bt->T, Tp, ws, &w);
-  LFI_REQUIRE(ws_bytes >= w.bytes + lfi_gemm_ws_bytes(), LFI_ERR_WORKSPACE, "feature workspace too small");
+  LFI_REQUIRE(ws_bytes >= w.bytes + gemm_scratch_bound(s, d, (size_t)Tp * bt->B, (size_t)bt->B * bt->T, gemm_mode), LFI_ERR_WORKSPACE,
+              "feature workspace too small");
   void *gws = (char *)ws + w.bytes;
   return build_cond(s, d, p, bt, t0, Tp, cond, w.enc, w.gh, false, false, true, gemm_mode, gws, ws_bytes - w.bytes, st);
 }
 
-size_t lfi_sample_ws_bytes(const lfi_shape *s, int B, int T, int chunk) {
+size_t lfi_sample_ws_bytes(const lfi_shape *s, int B, int T, int chunk, int gemm_mode) {
   Dims d;
   if (make_dims(s, &d) != LFI_OK || B < 1 || chunk < 1) return 0;
   SampleWs w;
   plan_sample(s, d, B, T, chunk, nullptr, &w);
-  return w.bytes + lfi_gemm_ws_bytes();
+  return w.bytes + gemm_scratch_bound(s, d, (size_t)chunk * B, (size_t)B * T, gemm_mode);
 }
 
 int lfi_seq_sample(const lfi_shape *s, const void *derived, const lfi_params *p, const lfi_batch *bt, int seq_len,
@@ -422,8 +439,8 @@ int lfi_seq_sample(const lfi_shape *s, const void *derived, const lfi_params *p,
   const int B = bt->B, T = bt->T, Tgen = seq_len - d.start_ts, K = d.K;
   SampleWs w;
   plan_sample(s, d, B, T, chunk, ws, &w);
-  LFI_REQUIRE(ws_bytes >= w.bytes + lfi_gemm_ws_bytes(), LFI_ERR_WORKSPACE, "sample workspace too small: %zu < %zu", ws_bytes,
-              w.bytes + lfi_gemm_ws_bytes());
+  const size_t gneed = gemm_scratch_bound(s, d, (size_t)chunk * B, (size_t)B * T, gemm_mode);
+  LFI_REQUIRE(ws_bytes >= w.bytes + gneed, LFI_ERR_WORKSPACE, "sample workspace too small: %zu < %zu", ws_bytes, w.bytes + gneed);
   void *gws = (char *)ws + w.bytes;
   const size_t gws_bytes = ws_bytes - w.bytes;
   const DerivedLayout L = derived_layout(d);
@@ -471,7 +488,7 @@ size_t lfi_flowstep_ws_bytes(const lfi_shape *s, int B) {
   b.take<float>((size_t)B * d.GH);
   b.take<float>((size_t)B * d.C * 2);
   b.take<float>((size_t)B);
-  return round_up_sz(b.off, 256) + lfi_gemm_ws_bytes();
+  return round_up_sz(b.off, 256) + 256;
 }
 
 int lfi_flowstep(const lfi_shape *s, const void *derived, const lfi_params *p, int k, int reverse, const float *x,

@@ -260,7 +260,7 @@ class Engine:
         dev = self.theta.device
         z = torch.empty(Tp, B, self.C, dtype=torch.float32, device=dev)
         nll = torch.empty(Tp, B, dtype=torch.float32, device=dev)
-        ws = self._workspace(("train", B, T), L.lfi_train_ws_bytes(ctypes.byref(self.shape), B, T))
+        ws = self._workspace(("train", B, T), L.lfi_train_ws_bytes(ctypes.byref(self.shape), B, T, self.gemm_mode))
         cabi.check(L.lfi_seq_train_fwd(ctypes.byref(self.shape), self._derived.data_ptr(), ctypes.byref(P), ctypes.byref(bt),
                                        z.data_ptr(), nll.data_ptr(), scale_out.data_ptr() if scale_out is not None else None,
                                        ws.data_ptr(), ws.numel(), self.gemm_mode, st), "lfi_seq_train_fwd")
@@ -348,7 +348,7 @@ class Engine:
             if tuple(noise.shape) != (Tgen, B, self.C):
                 raise RuntimeError("noise must be [%d, %d, %d], got %s" % (Tgen, B, self.C, tuple(noise.shape)))
         logdet = torch.zeros(Tgen, B, dtype=torch.float32, device=dev) if want_logdet else None
-        ws = self._workspace(("sample", B, T, chunk), L.lfi_sample_ws_bytes(ctypes.byref(self.shape), B, T, chunk))
+        ws = self._workspace(("sample", B, T, chunk), L.lfi_sample_ws_bytes(ctypes.byref(self.shape), B, T, chunk, self.gemm_mode))
         cabi.check(L.lfi_seq_sample(ctypes.byref(self.shape), self._derived.data_ptr(), ctypes.byref(P), ctypes.byref(bt), seq_len,
                                     noise.data_ptr() if noise is not None else None, faces.data_ptr(),
                                     logdet.data_ptr() if logdet is not None else None, int(teacher_forced), int(chunk),
@@ -365,7 +365,7 @@ class Engine:
         B, T = x0.shape[0], x0.shape[1]
         bt, keep = self._batch_struct(data, B, T, masks)
         cond = torch.empty(Tp * B, self.Fe, dtype=torch.float32, device=self.theta.device)
-        ws = self._workspace(("feat", B, T, Tp), L.lfi_feature_ws_bytes(ctypes.byref(self.shape), B, T, Tp))
+        ws = self._workspace(("feat", B, T, Tp), L.lfi_feature_ws_bytes(ctypes.byref(self.shape), B, T, Tp, self.gemm_mode))
         cabi.check(L.lfi_feature_encode(ctypes.byref(self.shape), ctypes.byref(P), ctypes.byref(bt), t0, Tp, cond.data_ptr(),
                                         ws.data_ptr(), ws.numel(), self.gemm_mode, st), "lfi_feature_encode")
         return cond

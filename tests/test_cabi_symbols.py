@@ -42,7 +42,7 @@ def test_binding_loads_and_reports_sizes():
     assert L.lfi_feature_dim_folded(ctypes.byref(sh)) == 920  # F_eff
     assert L.lfi_start_ts(ctypes.byref(sh)) == 24
     assert L.lfi_coupling_out(ctypes.byref(sh)) == 56
-    assert L.lfi_train_ws_bytes(ctypes.byref(sh), 256, 80) > 0
+    assert L.lfi_train_ws_bytes(ctypes.byref(sh), 256, 80, 0) > 0
     bad = _cabi.Shape()
     bad.C, bad.K, bad.H, bad.D, bad.G = 56, 16, 130, 512, 3   # H not a multiple of 4
     assert L.lfi_derived_bytes(ctypes.byref(bad)) == 0
