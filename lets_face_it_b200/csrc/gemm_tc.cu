@@ -31,10 +31,11 @@ namespace tc {
 constexpr int BM = 128;        // tile rows (UMMA M, cta_group::1)
 constexpr int BK = 64;         // bf16 elements per k-block = one 128-byte swizzle span
 constexpr int UK = 16;         // UMMA K for 16-bit operands
-constexpr int kThreads = 192;  // 6 warps
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kMaxStages = 8;
-constexpr int kEpiPitch = 33;
-constexpr int kEpiBytes = 4 * 32 * kEpiPitch * 4;
+constexpr int kEpiPitch = 20;  // floats; 32 rows x 16 columns per staging pass, conflict-free for 128-bit accesses
+constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch * 4;
 constexpr int kTmemCols = 512;  // two accumulator tiles of up to 256 columns
 constexpr int kSmemLimit = 225 * 1024;  // dynamic; leaves room for the 1 KB alignment reserve
 
@@ -49,6 +50,9 @@ struct Params {
   const float *bias; long sBias;
   const float *aux; int ldaux; long sAux;
   int epi;
+  // optional bf16 plane output of the final value (hi, and lo = bf16(v - hi) when o_lo != nullptr); C may then be null
+  __nv_bfloat16 *o_hi, *o_lo; int ldo; long sO;
+  int vec;  // all fp32 pointers / pitches allow 128-bit accesses
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -123,6 +127,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (sm_100 UMMA, 128-byte swizzle).  All fields in 16-byte units.
@@ -172,7 +185,7 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
@@ -253,46 +266,129 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // Warp w may read TMEM lanes [32*(w%4), +32).  Two warps share a lane quarter and take alternate 16-column
+    // passes: tcgen05.ld (thread = row) -> shared-memory transpose -> 128-bit global accesses in which four lanes
+    // cover 64 contiguous bytes of a row.  Operands of the read-modify-write epilogues are prefetched before the
+    // TMEM load so their latency overlaps it.
+    const int q = warp & 3, half = (warp - 2) >> 2;
     float *stg = epi_stage + (warp - 2) * 32 * kEpiPitch;
+    const int rr = lane & 7, cg = (lane >> 3) * 4;
+    const bool want_c = p.C != nullptr;
+    const bool rmw = (p.epi & LFI_EPI_ACCUM) && p.splitk == 1;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const TileCoord t = tile_coord(p, tile, nkb);
       const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
-      mbar_wait(&tfull[as], aph);
-      tc_fence_after();
-      float *C = p.C + (size_t)t.b * p.sC;
-      const float *bias = p.bias ? p.bias + (size_t)t.b * p.sBias : nullptr;
-      const float *aux = p.aux ? p.aux + (size_t)t.b * p.sAux : nullptr;
+      float *C = want_c ? p.C + (size_t)t.b * p.sC : nullptr;
+      const float *bias = (p.epi & LFI_EPI_BIAS) ? p.bias + (size_t)t.b * p.sBias : nullptr;
+      const float *aux = (p.epi & LFI_EPI_LRELU_BWD) ? p.aux + (size_t)t.b * p.sAux : nullptr;
+      __nv_bfloat16 *ohi = p.o_hi ? p.o_hi + (size_t)t.b * p.sO : nullptr;
+      __nv_bfloat16 *olo = p.o_lo ? p.o_lo + (size_t)t.b * p.sO : nullptr;
       const bool has_work = t.kb1 > t.kb0;
-      for (int c = 0; c < p.bn / 32; ++c) {
-        const int n = t.n0 + c * 32 + lane;
-        if (t.n0 + c * 32 >= p.N) break;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + c * 32, v);
-        tmem_ld_wait();
+      const int mrow0 = t.m0 + q * 32;
+      bool waited = false;
+      for (int sc = half; sc < p.bn / 16; sc += 2) {
+        const int nc0 = t.n0 + sc * 16;
+        if (nc0 >= p.N) break;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + sc * 16;
+        if (p.vec) {
+          const int n = nc0 + cg;  // N % 4 == 0 in vec mode: a 4-group is entirely inside or outside
+          const bool ncol_ok = n < p.N;
+          float4 pre[4];
+          if (ncol_ok && (rmw || aux)) {
+            const float *src = rmw ? C : aux;
+            const int ld = rmw ? p.ldc : p.ldaux;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * kEpiPitch + j] = __uint_as_float(v[j]);
-        __syncwarp();
-        const float bv = (bias && n < p.N && (p.epi & LFI_EPI_BIAS)) ? bias[n] : 0.f;
-        if (n < p.N) {
-#pragma unroll 4
-          for (int r = 0; r < 32; ++r) {
-            const int m = t.m0 + q * 32 + r;
-            if (m >= p.M) break;
-            float x = has_work ? stg[r * kEpiPitch + lane] : 0.f;
-            x += bv;
-            if (p.epi & LFI_EPI_LRELU) x = x > 0.f ? x : kLeaky * x;
-            if (p.epi & LFI_EPI_LRELU_BWD) x *= (aux[(size_t)m * p.ldaux + n] > 0.f ? 1.f : kLeaky);
-            float *dst = C + (size_t)m * p.ldc + n;
-            if (p.splitk > 1) atomicAdd(dst, x);
-            else if (p.epi & LFI_EPI_ACCUM) *dst += x;
-            else *dst = x;
+            for (int i = 0; i < 4; ++i) {
+              const int m = mrow0 + rr + 8 * i;
+              pre[i] = m < p.M ? *reinterpret_cast<const float4 *>(src + (size_t)m * ld + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias && ncol_ok) bv = *reinterpret_cast<const float4 *>(bias + n);
+          if (!waited) { mbar_wait(&tfull[as], aph); tc_fence_after(); waited = true; }
+          uint32_t v[16];
+          tmem_ld16(taddr, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4 *>(&stg[lane * kEpiPitch + 4 * j]) =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          __syncwarp();
+          if (ncol_ok) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = rr + 8 * i, m = mrow0 + r;
+              if (m >= p.M) break;
+              float4 x4 = *reinterpret_cast<const float4 *>(&stg[r * kEpiPitch + cg]);
+              float x[4] = {x4.x, x4.y, x4.z, x4.w};
+              const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+              const float a4[4] = {pre[i].x, pre[i].y, pre[i].z, pre[i].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float y = has_work ? x[e] : 0.f;
+                y += b4[e];
+                if (p.epi & LFI_EPI_LRELU) y = y > 0.f ? y : kLeaky * y;
+                if (aux) y *= (a4[e] > 0.f ? 1.f : kLeaky);
+                if (rmw) y += a4[e];
+                x[e] = y;
+              }
+              if (want_c) {
+                float *dst = C + (size_t)m * p.ldc + n;
+                if (p.splitk > 1) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) atomicAdd(dst + e, x[e]);
+                } else {
+                  *reinterpret_cast<float4 *>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                }
+              }
+              if (ohi) {
+                __align__(8) __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  h4[e] = __float2bfloat16_rn(x[e]);
+                  l4[e] = __float2bfloat16_rn(x[e] - __bfloat162float(h4[e]));
+                }
+                const size_t o = (size_t)m * p.ldo + n;
+                *reinterpret_cast<uint2 *>(ohi + o) = *reinterpret_cast<const uint2 *>(h4);
+                if (olo) *reinterpret_cast<uint2 *>(olo + o) = *reinterpret_cast<const uint2 *>(l4);
+              }
+            }
+          }
+          __syncwarp();
+        } else {
+          // generic path (odd pitches / unaligned bases): thread = row, scalar accesses
+          if (!waited) { mbar_wait(&tfull[as], aph); tc_fence_after(); waited = true; }
+          uint32_t v[16];
+          tmem_ld16(taddr, v);
+          tmem_ld_wait();
+          const int m = mrow0 + lane;
+          if (m < p.M) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = nc0 + j;
+              if (n >= p.N) break;
+              float y = has_work ? __uint_as_float(v[j]) : 0.f;
+              if (bias) y += bias[n];
+              if (p.epi & LFI_EPI_LRELU) y = y > 0.f ? y : kLeaky * y;
+              if (aux) y *= (aux[(size_t)m * p.ldaux + n] > 0.f ? 1.f : kLeaky);
+              if (want_c) {
+                float *dst = C + (size_t)m * p.ldc + n;
+                if (p.splitk > 1) atomicAdd(dst, y);
+                else if (p.epi & LFI_EPI_ACCUM) *dst += y;
+                else *dst = y;
+              }
+              if (ohi) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(y);
+                ohi[(size_t)m * p.ldo + n] = h;
+                if (olo) olo[(size_t)m * p.ldo + n] = __float2bfloat16_rn(y - __bfloat162float(h));
+              }
+            }
           }
         }
-        __syncwarp();
       }
+      if (!waited) { mbar_wait(&tfull[as], aph); tc_fence_after(); }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -417,6 +513,13 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   }
   p.C = g.C; p.ldc = g.ldc; p.sC = g.sC; p.bias = g.bias; p.sBias = g.sBias; p.aux = g.aux; p.ldaux = g.ldaux; p.sAux = g.sAux;
   p.epi = g.epi;
+  p.o_hi = (__nv_bfloat16 *)g.pOut.hi; p.o_lo = (__nv_bfloat16 *)g.pOut.lo; p.ldo = g.pOut.ld; p.sO = g.pOut.stride;
+  auto al16 = [](const void *q) { return ((uintptr_t)q & 15) == 0; };
+  p.vec = g.N % 4 == 0;
+  if (g.C) p.vec = p.vec && al16(g.C) && g.ldc % 4 == 0 && g.sC % 4 == 0;
+  if (g.epi & LFI_EPI_BIAS) p.vec = p.vec && al16(g.bias) && g.sBias % 4 == 0;
+  if (g.epi & LFI_EPI_LRELU_BWD) p.vec = p.vec && al16(g.aux) && g.ldaux % 4 == 0 && g.sAux % 4 == 0;
+  if (g.pOut.hi) p.vec = p.vec && al16(g.pOut.hi) && (!g.pOut.lo || al16(g.pOut.lo)) && g.pOut.ld % 4 == 0 && g.pOut.stride % 4 == 0;
 
   CUtensorMap mA0, mA1, mB0, mB1;
   const int a_box = A.mn ? BK : BM, b_box = B.mn ? BK : p.bn;
@@ -476,9 +579,10 @@ int gemm_tc(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t
   if (!gemm_tc_wants(g)) return LFI_OK;
   const int nplanes = mode == LFI_GEMM_BF16X3 ? 2 : 1;
   const size_t need = tc::split_ws_bytes(g, nplanes);
-  LFI_REQUIRE(ws && ws_bytes >= need, LFI_ERR_WORKSPACE, "gemm_tc: operand-plane workspace too small (%zu < %zu) for %dx%dx%d b=%d", ws_bytes, need,
-              g.M, g.N, g.K, g.batch);
-  LFI_REQUIRE(g.A && g.B && g.C, LFI_ERR_ARG, "gemm: null operand");
+  LFI_REQUIRE((g.pA.hi && g.pB.hi) || (ws && ws_bytes >= need), LFI_ERR_WORKSPACE,
+              "gemm_tc: operand-plane workspace too small (%zu < %zu) for %dx%dx%d b=%d", ws_bytes, need, g.M, g.N, g.K, g.batch);
+  LFI_REQUIRE((g.A || g.pA.hi) && (g.B || g.pB.hi) && (g.C || g.pOut.hi), LFI_ERR_ARG, "gemm: null operand");
+  LFI_REQUIRE(nplanes == 1 || ((!g.pA.hi || g.pA.lo) && (!g.pB.hi || g.pB.lo)), LFI_ERR_ARG, "gemm: split-bf16 mode needs lo planes");
   LFI_REQUIRE(!(g.epi & LFI_EPI_BIAS) || g.bias, LFI_ERR_ARG, "gemm: bias epilogue without bias");
   LFI_REQUIRE(!(g.epi & LFI_EPI_LRELU_BWD) || g.aux, LFI_ERR_ARG, "gemm: lrelu-bwd epilogue without aux");
   // A: transA = 0 -> stored [M, K] (K-major); 1 -> stored [K, M] (MN-major).  B: transB = 1 -> [N, K] (K-major); 0 -> [K, N] (MN-major)
@@ -491,9 +595,18 @@ int gemm_tc(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t
   const size_t ae = tc::plane_elems(A.rows, A.cols, g.batch), be = tc::plane_elems(B.rows, B.cols, g.batch);
   __nv_bfloat16 *a_hi = base, *a_lo = nplanes == 2 ? base + ae : nullptr;
   __nv_bfloat16 *b_hi = base + ae * nplanes, *b_lo = nplanes == 2 ? b_hi + be : nullptr;
-  LFI_TRY(tc::split(g.A, A.rows, A.cols, g.lda, g.sA, g.batch, a_hi, a_lo, st));
-  LFI_TRY(tc::split(g.B, B.rows, B.cols, g.ldb, g.sB, g.batch, b_hi, b_lo, st));
-  A.hi = a_hi; A.lo = a_lo; B.hi = b_hi; B.lo = b_lo;
+  if (g.pA.hi) {
+    A.hi = (const __nv_bfloat16 *)g.pA.hi; A.lo = nplanes == 2 ? (const __nv_bfloat16 *)g.pA.lo : nullptr; A.ldp = g.pA.ld; A.stride = g.pA.stride;
+  } else {
+    LFI_TRY(tc::split(g.A, A.rows, A.cols, g.lda, g.sA, g.batch, a_hi, a_lo, st));
+    A.hi = a_hi; A.lo = a_lo;
+  }
+  if (g.pB.hi) {
+    B.hi = (const __nv_bfloat16 *)g.pB.hi; B.lo = nplanes == 2 ? (const __nv_bfloat16 *)g.pB.lo : nullptr; B.ldp = g.pB.ld; B.stride = g.pB.stride;
+  } else {
+    LFI_TRY(tc::split(g.B, B.rows, B.cols, g.ldb, g.sB, g.batch, b_hi, b_lo, st));
+    B.hi = b_hi; B.lo = b_lo;
+  }
   LFI_TRY(tc::launch_core(A, B, g, nplanes, st));
   *handled = true;
   return LFI_OK;

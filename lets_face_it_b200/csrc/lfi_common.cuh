@@ -117,6 +117,13 @@ struct Bump {
 };
 
 // ---- generic GEMM (gemm_simt.cu / gemm_tc.cu) ---------------------------------------------------
+// bf16 operand planes of the tensor-core modes: value = hi (+ lo in the split-bf16 x3 mode); layout as the fp32
+// operand they stand for (same rows / cols / transposition), pitch ld in elements (multiple of 8), 16-byte aligned.
+struct PlaneRef {
+  const void *hi, *lo;
+  int ld; long stride;
+};
+
 struct GemmArgs {
   int transA, transB, M, N, K;
   const float *A; int lda; long sA;
@@ -125,6 +132,8 @@ struct GemmArgs {
   const float *bias; long sBias;
   const float *aux; int ldaux; long sAux;
   int batch, epi;
+  PlaneRef pA, pB;  // hi != nullptr: operand already split (A / B may then be null); tensor-core modes only
+  PlaneRef pOut;    // hi != nullptr: also emit the result as bf16 planes (C may then be null); tensor-core modes only
 };
 int gemm_simt(const GemmArgs &g, cudaStream_t st);
 int gemm_dispatch(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st);
