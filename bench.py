@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--gemm", default=os.environ.get("LFI_GEMM", "fp32"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=32, help="sequences per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--no-sample", action="store_true")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling helper: warm up, then run ONE step between cudaProfilerStart/Stop and exit "
@@ -148,7 +149,7 @@ def run_reference(a):
     if rank != 0:
         return
     hp = load_hparams()
-    Bs = 32
+    Bs = a.ref_batch
     step, frames = cpu_reference_step_fn(hp, Bs, T_TRAIN)
     for _ in range(a.warmup):
         step()
@@ -252,7 +253,7 @@ def run_ours(a):
     def e2e_step():
         db = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         loss = trainer.step(db)
-        return float(loss)   # device -> host read of the step's result
+        return float(loss.detach())   # device -> host read of the step's result
 
     for _ in range(2):
         e2e_step()

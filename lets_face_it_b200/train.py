@@ -64,8 +64,7 @@ class Trainer:
         self.gflat.zero_()
         eng.train_backward(z, self._dnll[key], self.gflat)
         g = self.gflat[:eng.n_theta]
-        if self.world > 1:
-            torch.distributed.all_reduce(g, group=self.pg)  # sum; averaged by grad_scale below
+        allreduce_flat_gradient(g, self.world, self.pg)  # sum; averaged by grad_scale below
         self.step_count += 1
         cabi.check(cabi.lib().lfi_clip_adam(eng.theta.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), eng.n_theta,
                                             self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0 / self.world,
@@ -75,6 +74,15 @@ class Trainer:
     def grad_norm(self):
         """Global gradient norm of the last step (after the all-reduce average, before clipping)."""
         return torch.sqrt(self.scratch[0]) / self.world
+
+
+def allreduce_flat_gradient(g, world, group=None):
+    """The one exchange of the path: SUM all-reduce of the flat fp32 gradient over the ranks.
+    The mean over the global batch is restored by `grad_scale = 1/world` in the fused clip+Adam (every rank holds an
+    equal shard and the reference loss is a batch mean, models.py:555), so clipping sees the global-batch gradient."""
+    if world > 1:
+        torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.SUM, group=group)
+    return g
 
 
 def shard_batch(batch, rank, world):
