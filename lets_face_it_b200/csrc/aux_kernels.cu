@@ -3,6 +3,7 @@
 // All are coalesced, grid-stride where the size warrants it, warp-shuffle reduced.
 #include "aux_kernels.cuh"
 #include <cmath>
+#include <cuda_bf16.h>
 
 namespace lfi {
 namespace aux {
@@ -202,6 +203,11 @@ __global__ void enc_gate_fwd_kernel(EncStep a) {
     if (a.gates) { float *g = a.gates + m * 3 * E; g[e] = rg; g[E + e] = ug; g[2 * E + e] = ng; }
     if (a.ahn) a.ahn[idx] = ahn;
     if (a.cond) a.cond[m * a.cond_ld + e] = h;
+    if (a.h_hi) {
+      const __nv_bfloat16 hh = __float2bfloat16_rn(h);
+      ((__nv_bfloat16 *)a.h_hi)[idx] = hh;
+      if (a.h_lo) ((__nv_bfloat16 *)a.h_lo)[idx] = __float2bfloat16_rn(h - __bfloat162float(hh));
+    }
   }
 }
 int enc_gate_fwd(const EncStep &a, cudaStream_t st) {
@@ -232,6 +238,51 @@ __global__ void enc_gate_bwd_kernel(EncStepBwd a) {
 }
 int enc_gate_bwd(const EncStepBwd &a, cudaStream_t st) {
   enc_gate_bwd_kernel<<<blocks_for((size_t)a.M * a.E), TB, 0, st>>>(a);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+// thread = hidden unit e (coalesced over e), block = a strip of rows; the four bias-gradient sums stay in registers
+__global__ void enc_gate_bwd2_kernel(EncStepBwd2 a, int rows_per_block) {
+  const int E = a.E;
+  const int e = blockIdx.y * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(a.M, r0 + rows_per_block);
+  float s_r = 0.f, s_u = 0.f, s_n = 0.f, s_nr = 0.f;
+  __nv_bfloat16 *dah_hi = (__nv_bfloat16 *)a.dah_hi, *dah_lo = (__nv_bfloat16 *)a.dah_lo;
+  __nv_bfloat16 *dan_hi = (__nv_bfloat16 *)a.dan_hi, *dan_lo = (__nv_bfloat16 *)a.dan_lo;
+  auto put = [](__nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t o, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[o] = h;
+    if (lo) lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+  };
+  for (int m = r0; m < r1; ++m) {
+    const size_t idx = (size_t)m * E + e, g3 = (size_t)m * 3 * E;
+    float dh = a.dh[idx];
+    if (a.dh_extra) dh += a.dh_extra[(size_t)m * a.dh_extra_ld + e];
+    const float rg = a.gates[g3 + e], ug = a.gates[g3 + E + e], ng = a.gates[g3 + 2 * E + e];
+    const float hp = a.hprev ? a.hprev[idx] : 0.f;
+    const float an = a.ahn[idx];
+    const float dn = dh * (1.0f - ug), du = dh * (hp - ng);
+    const float dan = dn * (1.0f - ng * ng), dau = du * ug * (1.0f - ug), dar = dan * an * rg * (1.0f - rg);
+    const float danr = dan * rg;
+    if (a.dah32) { a.dah32[g3 + e] = dar; a.dah32[g3 + E + e] = dau; a.dah32[g3 + 2 * E + e] = danr; a.dan32[idx] = dan; }
+    if (dah_hi) {
+      put(dah_hi, dah_lo, g3 + e, dar); put(dah_hi, dah_lo, g3 + E + e, dau); put(dah_hi, dah_lo, g3 + 2 * E + e, danr);
+      put(dan_hi, dan_lo, idx, dan);
+    }
+    a.dh[idx] = dh * ug;
+    s_r += dar; s_u += dau; s_n += dan; s_nr += danr;
+  }
+  atomicAdd(a.gb_ih + e, s_r); atomicAdd(a.gb_ih + E + e, s_u); atomicAdd(a.gb_ih + 2 * E + e, s_n);
+  atomicAdd(a.gb_hh + e, s_r); atomicAdd(a.gb_hh + E + e, s_u); atomicAdd(a.gb_hh + 2 * E + e, s_nr);
+}
+int enc_gate_bwd2(const EncStepBwd2 &a, cudaStream_t st) {
+  const int threads = a.E >= 256 ? 256 : (a.E >= 128 ? 128 : 64);
+  const int cb = (a.E + threads - 1) / threads;
+  int rpb = 32;
+  while ((long)((a.M + rpb - 1) / rpb) * cb > 148 * 16 && rpb < 4096) rpb *= 2;
+  enc_gate_bwd2_kernel<<<dim3((a.M + rpb - 1) / rpb, cb), threads, 0, st>>>(a, rpb);
   LFI_LAUNCH_CHECK();
   return LFI_OK;
 }

@@ -39,6 +39,7 @@ struct EncStep {
   float *h;             // [M][E]
   float *gates, *ahn;   // [M][3E], [M][E] stash (nullable)
   float *cond; int cond_ld;  // final step: also written to cond[m*cond_ld + e] (nullable)
+  void *h_hi, *h_lo;    // optional bf16 planes of h [M][E] (tensor-core modes: next step's GEMM operand, dW_hh operand)
   int s, hist, B, T, Tp, t0, E;
 };
 int enc_gate_fwd(const EncStep &a, cudaStream_t st);
@@ -51,6 +52,21 @@ struct EncStepBwd {
   int M, E;
 };
 int enc_gate_bwd(const EncStepBwd &a, cudaStream_t st);
+
+// Gate backward of one window step for all M windows, writing the gate gradients in the form the batched weight-gradient
+// GEMMs consume (fp32, or bf16 planes in the tensor-core modes) and accumulating the bias gradients in-kernel:
+//   dah [M][3E] = (da_r, da_u, da_n * r)   (h-side pre-activations: dW_hh, dh_prev, db_hh)
+//   dan [M][E]  =  da_n                    (i-side n block: dW_ih rows [2E,3E), db_ih)
+struct EncStepBwd2 {
+  const float *gates, *ahn, *hprev;
+  float *dh;
+  const float *dh_extra; int dh_extra_ld;
+  float *dah32, *dan32;                      // fp32 outputs (nullable)
+  void *dah_hi, *dah_lo, *dan_hi, *dan_lo;   // bf16 plane outputs (nullable; lo nullable)
+  float *gb_ih, *gb_hh;                      // [3E] bias gradients, accumulated
+  int M, E;
+};
+int enc_gate_bwd2(const EncStepBwd2 &a, cudaStream_t st);
 
 // LU parametrisation helpers (modules.py:163-177)
 int lu_build(float *Lm, float *Um, const float *l, const float *u, const float *log_s, const float *sign_s, int K, int C, cudaStream_t st);

@@ -567,7 +567,10 @@ static int split(const float *src, int rows, int cols, int ld, long stride, int 
 
 }  // namespace tc
 
-size_t gemm_tc_ws_bytes() { return 0; }
+// fp32 [batch][rows][cols] (pitch ld) -> bf16 planes [batch][rows][round_up(cols, 8)] (hi, and lo when non-null)
+int split_to_planes(const float *src, int rows, int cols, int ld, long stride, int batch, void *hi, void *lo, cudaStream_t st) {
+  return tc::split(src, rows, cols, ld, stride, batch, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, st);
+}
 
 bool gemm_tc_wants(const GemmArgs &g) {
   // tiny contractions stay on the exact fp32 tiles (nothing to win, and the 1x1-conv / LU helpers need fp32)
@@ -576,7 +579,7 @@ bool gemm_tc_wants(const GemmArgs &g) {
 
 int gemm_tc(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st, bool *handled) {
   *handled = false;
-  if (!gemm_tc_wants(g)) return LFI_OK;
+  if (!g.pA.hi && !g.pB.hi && !gemm_tc_wants(g)) return LFI_OK;  // operands already in plane form always run here
   const int nplanes = mode == LFI_GEMM_BF16X3 ? 2 : 1;
   const size_t need = tc::split_ws_bytes(g, nplanes);
   LFI_REQUIRE((g.pA.hi && g.pB.hi) || (ws && ws_bytes >= need), LFI_ERR_WORKSPACE,

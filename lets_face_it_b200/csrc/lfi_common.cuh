@@ -137,6 +137,9 @@ struct GemmArgs {
 };
 int gemm_simt(const GemmArgs &g, cudaStream_t st);
 int gemm_dispatch(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st);
+bool gemm_tc_wants(const GemmArgs &g);
+int split_to_planes(const float *src, int rows, int cols, int ld, long stride, int batch, void *hi, void *lo, cudaStream_t st);
+inline PlaneRef plane_ref(const void *hi, const void *lo, int ld, long stride = 0) { PlaneRef r; r.hi = hi; r.lo = lo; r.ld = ld; r.stride = stride; return r; }
 
 inline GemmArgs gemm_args(int tA, int tB, int M, int N, int K, const float *A, int lda, const float *B, int ldb,
                           float *C, int ldc, int epi = 0, const float *bias = nullptr) {

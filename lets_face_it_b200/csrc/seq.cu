@@ -74,7 +74,25 @@ struct EncWs {
   float *hs;     // [hist][M][E]   (training) or [2][M][E] ping-pong (sampling)
   float *gates;  // [hist][M][3E]  (training only)
   float *ahn;    // [hist][M][E]   (training only)
+  // tensor-core modes (planes == true): bf16 operand planes written by the producers themselves, never re-split
+  bool planes;
+  void *hp_hi, *hp_lo;    // h          [hist | 2][M][E]
+  void *whh_hi, *whh_lo;  // W_hh       [3E][E]  (K-major B of the step GEMM, MN-major B of dh_prev = dA_h W_hh)
+  // backward (training only): gate gradients of every window step, kept for the batched weight-gradient GEMMs
+  float *dah32, *dan32;   // fp32 mode: [hist][M][3E], [hist][M][E]
+  void *dah_hi, *dah_lo, *dan_hi, *dan_lo;  // planes, same shapes
+  void *xg_hi, *xg_lo;    // masked window inputs [hist][M][round_up(dim, 8)]
 };
+
+// A modality's encoder runs on operand planes when every GEMM it issues is taken by the tcgen05 tiles.
+static bool enc_use_planes(const lfi_shape *s, int m, size_t M, int mode) {
+  if (mode == LFI_GEMM_FP32) return false;
+  const int E = s->ehid[m], dim = s->dim[m];
+  if (E < 32 || E % 8 != 0 || dim < 16 || M < 128) return false;
+  GemmArgs g = gemm_args(0, 1, (int)M, 3 * E, E, nullptr, E, nullptr, E, nullptr, 3 * E);
+  return gemm_tc_wants(g);
+}
+static void *take_bf16(Bump &b, size_t n) { return (void *)b.take<uint16_t>(n); }
 struct TrainWs {
   float *cond, *Cact, *G, *ld, *gh;
   EncWs enc[LFI_NMOD];
@@ -84,7 +102,7 @@ struct TrainWs {
   size_t bytes;
 };
 
-static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, void *ws, TrainWs *w) {
+static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode, void *ws, TrainWs *w) {
   Bump b(ws, 0);
   const size_t Tp = T - d.start_ts, M = Tp * B, K = d.K;
   w->cond = b.take<float>(M * d.Fe);
@@ -93,13 +111,27 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, void *ws
   w->ld = b.take<float>(M);
   size_t ghmax = 0, xgmax = 0, emax = 0;
   for (int m = 0; m < LFI_NMOD; ++m) {
-    w->enc[m] = EncWs{nullptr, nullptr, nullptr, nullptr};
+    memset(&w->enc[m], 0, sizeof(EncWs));
     if (s->hist[m] <= 0 || s->ehid[m] <= 0) continue;
     const size_t E = s->ehid[m], h = s->hist[m];
-    w->enc[m].xp = b.take<float>((size_t)B * T * 3 * E);
-    w->enc[m].hs = b.take<float>(h * M * E);
-    w->enc[m].gates = b.take<float>(h * M * 3 * E);
-    w->enc[m].ahn = b.take<float>(h * M * E);
+    EncWs &e = w->enc[m];
+    e.xp = b.take<float>((size_t)B * T * 3 * E);
+    e.hs = b.take<float>(h * M * E);
+    e.gates = b.take<float>(h * M * 3 * E);
+    e.ahn = b.take<float>(h * M * E);
+    e.planes = enc_use_planes(s, m, M, mode);
+    if (e.planes) {
+      const bool lo = mode == LFI_GEMM_BF16X3;
+      const size_t dimp = round_up(s->dim[m], 8);
+      e.hp_hi = take_bf16(b, h * M * E);            e.hp_lo = lo ? take_bf16(b, h * M * E) : nullptr;
+      e.whh_hi = take_bf16(b, 3 * E * E);           e.whh_lo = lo ? take_bf16(b, 3 * E * E) : nullptr;
+      e.dah_hi = take_bf16(b, h * M * 3 * E);       e.dah_lo = lo ? take_bf16(b, h * M * 3 * E) : nullptr;
+      e.dan_hi = take_bf16(b, h * M * E);           e.dan_lo = lo ? take_bf16(b, h * M * E) : nullptr;
+      e.xg_hi = take_bf16(b, h * M * dimp);         e.xg_lo = lo ? take_bf16(b, h * M * dimp) : nullptr;
+    } else {
+      e.dah32 = b.take<float>(h * M * 3 * E);
+      e.dan32 = b.take<float>(h * M * E);
+    }
     if (M * 3 * E > ghmax) ghmax = M * 3 * E;
     if (h * M * s->dim[m] > xgmax) xgmax = h * M * s->dim[m];
     if (E > emax) emax = E;
@@ -127,8 +159,7 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, void *ws
   w->dWcF = b.take<float>(K * d.D * d.Fe);
   w->xg = b.take<float>(xgmax);
   w->dhe = b.take<float>(M * emax);
-  w->dai = b.take<float>(ghmax);
-  w->dah = b.take<float>(ghmax);
+  w->dai = nullptr; w->dah = nullptr;
   w->bytes = round_up_sz(b.off, 256);
 }
 
@@ -156,20 +187,31 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
       GemmArgs g = gemm_args(0, 1, B * T, 3 * E, dim, bt->x[m], dim, p->enc_w_ih[m], dim, enc[m].xp, 3 * E);
       LFI_TRY(gemm_dispatch(mode, g, gws, gws_bytes, st));
     }
+    EncWs &ew = enc[m];
+    const bool lo = mode == LFI_GEMM_BF16X3;
+    if (ew.planes && project)  // W_hh planes: once per call (weights change every optimizer step)
+      LFI_TRY(split_to_planes(p->enc_w_hh[m], 3 * E, E, E, 0, 1, ew.whh_hi, lo ? ew.whh_lo : nullptr, st));
     for (int sidx = 0; sidx < hist; ++sidx) {
       float *hprev = nullptr, *hcur;
-      if (stash) { hcur = enc[m].hs + (size_t)sidx * M * E; if (sidx) hprev = enc[m].hs + (size_t)(sidx - 1) * M * E; }
-      else { hcur = enc[m].hs + (size_t)(sidx & 1) * M * E; if (sidx) hprev = enc[m].hs + (size_t)((sidx - 1) & 1) * M * E; }
+      const int cur = stash ? sidx : (sidx & 1), prv = stash ? sidx - 1 : ((sidx - 1) & 1);
+      hcur = ew.hs + (size_t)cur * M * E;
+      if (sidx) hprev = ew.hs + (size_t)prv * M * E;
       if (sidx) {
         GemmArgs gg = gemm_args(0, 1, (int)M, 3 * E, E, hprev, E, p->enc_w_hh[m], E, gh, 3 * E);
+        if (ew.planes) {
+          gg.pA = plane_ref((uint16_t *)ew.hp_hi + (size_t)prv * M * E, lo ? (uint16_t *)ew.hp_lo + (size_t)prv * M * E : nullptr, E);
+          gg.pB = plane_ref(ew.whh_hi, ew.whh_lo, E);
+        }
         LFI_TRY(gemm_dispatch(mode, gg, gws, gws_bytes, st));
       }
       aux::EncStep a;
-      a.xp = enc[m].xp; a.gh = sidx ? gh : nullptr; a.b_ih = p->enc_b_ih[m]; a.b_hh = p->enc_b_hh[m];
+      a.xp = ew.xp; a.gh = sidx ? gh : nullptr; a.b_ih = p->enc_b_ih[m]; a.b_hh = p->enc_b_hh[m];
       a.mask = bt->mask[m]; a.hprev = hprev; a.h = hcur;
-      a.gates = stash ? enc[m].gates + (size_t)sidx * M * 3 * E : nullptr;
-      a.ahn = stash ? enc[m].ahn + (size_t)sidx * M * E : nullptr;
+      a.gates = stash ? ew.gates + (size_t)sidx * M * 3 * E : nullptr;
+      a.ahn = stash ? ew.ahn + (size_t)sidx * M * E : nullptr;
       a.cond = (sidx == hist - 1) ? cond + d.enc_offe[m] : nullptr; a.cond_ld = d.Fe;
+      a.h_hi = ew.planes ? (void *)((uint16_t *)ew.hp_hi + (size_t)cur * M * E) : nullptr;
+      a.h_lo = (ew.planes && lo) ? (void *)((uint16_t *)ew.hp_lo + (size_t)cur * M * E) : nullptr;
       a.s = sidx; a.hist = hist; a.B = B; a.T = T; a.Tp = Tp; a.t0 = t0; a.E = E;
       LFI_TRY(aux::enc_gate_fwd(a, st));
     }
@@ -240,7 +282,7 @@ size_t lfi_train_ws_bytes(const lfi_shape *s, int B, int T, int gemm_mode) {
   Dims d;
   if (make_dims(s, &d) != LFI_OK || T <= d.start_ts || B < 1) return 0;
   TrainWs w;
-  plan_train(s, d, B, T, nullptr, &w);
+  plan_train(s, d, B, T, gemm_mode, nullptr, &w);
   return w.bytes + gemm_scratch_bound(s, d, (size_t)(T - d.start_ts) * B, (size_t)B * T, gemm_mode);
 }
 
@@ -254,7 +296,7 @@ int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params 
   const int B = bt->B, T = bt->T, Tp = T - d.start_ts;
   const size_t M = (size_t)Tp * B;
   TrainWs w;
-  plan_train(s, d, B, T, ws, &w);
+  plan_train(s, d, B, T, gemm_mode, ws, &w);
   const size_t gneed = gemm_scratch_bound(s, d, M, (size_t)B * T, gemm_mode);
   LFI_REQUIRE(ws_bytes >= w.bytes + gneed, LFI_ERR_WORKSPACE, "train workspace too small: %zu < %zu", ws_bytes, w.bytes + gneed);
   void *gws = (char *)ws + w.bytes;
@@ -287,7 +329,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   const int In = Ci + D;
   const size_t M = (size_t)Tp * B;
   TrainWs w;
-  plan_train(s, d, B, T, ws, &w);
+  plan_train(s, d, B, T, gemm_mode, ws, &w);
   LFI_REQUIRE(ws_bytes >= w.bytes + gemm_scratch_bound(s, d, M, (size_t)B * T, gemm_mode), LFI_ERR_WORKSPACE, "train workspace too small");
   void *gws = (char *)ws + w.bytes;
   const size_t gws_bytes = ws_bytes - w.bytes;
@@ -338,29 +380,52 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
     LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
   }
 
-  // 4. encoder GRUs, BPTT over the window (models.py:63-64)
+  // 4. encoder GRUs, BPTT over the window (models.py:63-64).  Per step only the gate math and dh_prev = dA_h W_hh
+  //    run; the gate gradients of all steps are kept so that every weight gradient is ONE long-K GEMM per modality
+  //    (reduction over hist x M rows), and the bias gradients are accumulated inside the gate kernel.
   for (int m = 0; m < LFI_NMOD; ++m) {
     const int hist = s->hist[m], E = s->ehid[m], dim = s->dim[m];
     if (hist <= 0 || E <= 0) continue;
+    EncWs &ew = w.enc[m];
+    const bool lo = gemm_mode == LFI_GEMM_BF16X3;
+    const int dimp = round_up(dim, 8);
     LFI_TRY(aux::gather_windows(w.xg, dim, 1, bt->x[m], bt->mask[m], B, T, dim, hist, 1, d.start_ts, Tp, st));
+    if (ew.planes) LFI_TRY(split_to_planes(w.xg, (int)(hist * M), dim, dim, 0, 1, ew.xg_hi, lo ? ew.xg_lo : nullptr, st));
     LFI_TRY(aux::fill(w.dhe, 0.f, M * E, st));
+    auto off16 = [](void *base, size_t n) -> void * { return base ? (void *)((uint16_t *)base + n) : nullptr; };
     for (int sidx = hist - 1; sidx >= 0; --sidx) {
-      aux::EncStepBwd e;
-      e.gates = w.enc[m].gates + (size_t)sidx * M * 3 * E; e.ahn = w.enc[m].ahn + (size_t)sidx * M * E;
-      e.hprev = sidx ? w.enc[m].hs + (size_t)(sidx - 1) * M * E : nullptr;
+      aux::EncStepBwd2 e;
+      memset(&e, 0, sizeof(e));
+      e.gates = ew.gates + (size_t)sidx * M * 3 * E; e.ahn = ew.ahn + (size_t)sidx * M * E;
+      e.hprev = sidx ? ew.hs + (size_t)(sidx - 1) * M * E : nullptr;
       e.dh = w.dhe; e.dh_extra = (sidx == hist - 1) ? w.dcond + d.enc_offe[m] : nullptr; e.dh_extra_ld = d.Fe;
-      e.dai = w.dai; e.dah = w.dah; e.M = (int)M; e.E = E;
-      LFI_TRY(aux::enc_gate_bwd(e, st));
-      LFI_TRY(aux::colsum(g->enc_b_ih[m], w.dai, 3 * E, (int)M, 3 * E, 1.0f, st));
-      LFI_TRY(aux::colsum(g->enc_b_hh[m], w.dah, 3 * E, (int)M, 3 * E, 1.0f, st));
-      GemmArgs q = gemm_args(1, 0, 3 * E, dim, (int)M, w.dai, 3 * E, w.xg + (size_t)sidx * M * dim, dim, g->enc_w_ih[m], dim, LFI_EPI_ACCUM);
-      LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
-      if (sidx) {
-        GemmArgs r = gemm_args(1, 0, 3 * E, E, (int)M, w.dah, 3 * E, e.hprev, E, g->enc_w_hh[m], E, LFI_EPI_ACCUM);
-        LFI_TRY(gemm_dispatch(gemm_mode, r, gws, gws_bytes, st));
-        GemmArgs t = gemm_args(0, 0, (int)M, E, 3 * E, w.dah, 3 * E, p->enc_w_hh[m], E, w.dhe, E, LFI_EPI_ACCUM);
+      if (ew.planes) {
+        e.dah_hi = off16(ew.dah_hi, (size_t)sidx * M * 3 * E); e.dah_lo = lo ? off16(ew.dah_lo, (size_t)sidx * M * 3 * E) : nullptr;
+        e.dan_hi = off16(ew.dan_hi, (size_t)sidx * M * E);     e.dan_lo = lo ? off16(ew.dan_lo, (size_t)sidx * M * E) : nullptr;
+      } else {
+        e.dah32 = ew.dah32 + (size_t)sidx * M * 3 * E; e.dan32 = ew.dan32 + (size_t)sidx * M * E;
+      }
+      e.gb_ih = g->enc_b_ih[m]; e.gb_hh = g->enc_b_hh[m]; e.M = (int)M; e.E = E;
+      LFI_TRY(aux::enc_gate_bwd2(e, st));
+      if (sidx) {  // dh_{s-1} += dA_h W_hh
+        GemmArgs t = gemm_args(0, 0, (int)M, E, 3 * E, e.dah32, 3 * E, p->enc_w_hh[m], E, w.dhe, E, LFI_EPI_ACCUM);
+        if (ew.planes) { t.pA = plane_ref(e.dah_hi, e.dah_lo, 3 * E); t.pB = plane_ref(ew.whh_hi, ew.whh_lo, E); }
         LFI_TRY(gemm_dispatch(gemm_mode, t, gws, gws_bytes, st));
       }
+    }
+    const int Kall = (int)(hist * M), Khh = (int)((hist - 1) * M);
+    if (hist > 1) {  // dW_hh += sum_{s>=1} dA_h[s]^T h[s-1]
+      GemmArgs q = gemm_args(1, 0, 3 * E, E, Khh, ew.dah32 ? ew.dah32 + M * 3 * E : nullptr, 3 * E, ew.hs, E, g->enc_w_hh[m], E, LFI_EPI_ACCUM);
+      if (ew.planes) { q.pA = plane_ref(off16(ew.dah_hi, M * 3 * E), lo ? off16(ew.dah_lo, M * 3 * E) : nullptr, 3 * E); q.pB = plane_ref(ew.hp_hi, ew.hp_lo, E); }
+      LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
+    }
+    {  // dW_ih rows [0,2E) += dA_h[:, :2E]^T x  (r, u blocks coincide with the i-side gradients); rows [2E,3E) += dA_n^T x
+      GemmArgs q = gemm_args(1, 0, 2 * E, dim, Kall, ew.dah32, 3 * E, w.xg, dim, g->enc_w_ih[m], dim, LFI_EPI_ACCUM);
+      if (ew.planes) { q.pA = plane_ref(ew.dah_hi, ew.dah_lo, 3 * E); q.pB = plane_ref(ew.xg_hi, ew.xg_lo, dimp); }
+      LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
+      GemmArgs r = gemm_args(1, 0, E, dim, Kall, ew.dan32, E, w.xg, dim, g->enc_w_ih[m] + (size_t)2 * E * dim, dim, LFI_EPI_ACCUM);
+      if (ew.planes) { r.pA = plane_ref(ew.dan_hi, ew.dan_lo, E); r.pB = plane_ref(ew.xg_hi, ew.xg_lo, dimp); }
+      LFI_TRY(gemm_dispatch(gemm_mode, r, gws, gws_bytes, st));
     }
   }
   return LFI_OK;
@@ -373,7 +438,7 @@ struct SampleWs {
   EncWs enc[LFI_NMOD];
   size_t bytes;
 };
-static void plan_sample(const lfi_shape *s, const Dims &d, int B, int T, int chunk, void *ws, SampleWs *w) {
+static void plan_sample(const lfi_shape *s, const Dims &d, int B, int T, int chunk, int mode, void *ws, SampleWs *w) {
   Bump b(ws, 0);
   const size_t Mc = (size_t)chunk * B, K = d.K;
   w->cond = b.take<float>(Mc * d.Fe);
@@ -383,11 +448,18 @@ static void plan_sample(const lfi_shape *s, const Dims &d, int B, int T, int chu
   w->cstate = d.G == 4 ? b.take<float>(K * B * d.H) : nullptr;
   size_t ghmax = 0;
   for (int m = 0; m < LFI_NMOD; ++m) {
-    w->enc[m] = EncWs{nullptr, nullptr, nullptr, nullptr};
+    memset(&w->enc[m], 0, sizeof(EncWs));
     if (s->hist[m] <= 0 || s->ehid[m] <= 0) continue;
     const size_t E = s->ehid[m];
-    w->enc[m].xp = b.take<float>((size_t)B * T * 3 * E);
-    w->enc[m].hs = b.take<float>(2 * Mc * E);
+    EncWs &e = w->enc[m];
+    e.xp = b.take<float>((size_t)B * T * 3 * E);
+    e.hs = b.take<float>(2 * Mc * E);
+    e.planes = enc_use_planes(s, m, Mc, mode);
+    if (e.planes) {
+      const bool lo = mode == LFI_GEMM_BF16X3;
+      e.hp_hi = take_bf16(b, 2 * Mc * E);  e.hp_lo = lo ? take_bf16(b, 2 * Mc * E) : nullptr;
+      e.whh_hi = take_bf16(b, 3 * E * E);  e.whh_lo = lo ? take_bf16(b, 3 * E * E) : nullptr;
+    }
     if (Mc * 3 * E > ghmax) ghmax = Mc * 3 * E;
   }
   w->gh = b.take<float>(ghmax);
@@ -399,7 +471,7 @@ size_t lfi_feature_ws_bytes(const lfi_shape *s, int B, int T, int Tp, int gemm_m
   Dims d;
   if (make_dims(s, &d) != LFI_OK || B < 1 || Tp < 1) return 0;
   SampleWs w;
-  plan_sample(s, d, B, T, Tp, nullptr, &w);
+  plan_sample(s, d, B, T, Tp, gemm_mode, nullptr, &w);
   return w.bytes + gemm_scratch_bound(s, d, (size_t)Tp * B, (size_t)B * T, gemm_mode);
 }
 
@@ -412,7 +484,7 @@ int lfi_feature_encode(const lfi_shape *s, const lfi_params *p, const lfi_batch 
   LFI_REQUIRE(t0 >= d.start_ts && t0 + Tp <= bt->T && Tp >= 1, LFI_ERR_SHAPE, "lfi_feature_encode: frames [%d,%d) outside [%d,%d)", t0,
               t0 + Tp, d.start_ts, bt->T);
   SampleWs w;
-  plan_sample(s, d, bt->B, bt->T, Tp, ws, &w);
+  plan_sample(s, d, bt->B, bt->T, Tp, gemm_mode, ws, &w);
   LFI_REQUIRE(ws_bytes >= w.bytes + gemm_scratch_bound(s, d, (size_t)Tp * bt->B, (size_t)bt->B * bt->T, gemm_mode), LFI_ERR_WORKSPACE,
               "feature workspace too small");
   void *gws = (char *)ws + w.bytes;
@@ -423,7 +495,7 @@ size_t lfi_sample_ws_bytes(const lfi_shape *s, int B, int T, int chunk, int gemm
   Dims d;
   if (make_dims(s, &d) != LFI_OK || B < 1 || chunk < 1) return 0;
   SampleWs w;
-  plan_sample(s, d, B, T, chunk, nullptr, &w);
+  plan_sample(s, d, B, T, chunk, gemm_mode, nullptr, &w);
   return w.bytes + gemm_scratch_bound(s, d, (size_t)chunk * B, (size_t)B * T, gemm_mode);
 }
 
@@ -438,7 +510,7 @@ int lfi_seq_sample(const lfi_shape *s, const void *derived, const lfi_params *p,
   LFI_REQUIRE(seq_len > d.start_ts, LFI_ERR_SHAPE, "seq_len=%d must exceed the longest history %d", seq_len, d.start_ts);
   const int B = bt->B, T = bt->T, Tgen = seq_len - d.start_ts, K = d.K;
   SampleWs w;
-  plan_sample(s, d, B, T, chunk, ws, &w);
+  plan_sample(s, d, B, T, chunk, gemm_mode, ws, &w);
   const size_t gneed = gemm_scratch_bound(s, d, (size_t)chunk * B, (size_t)B * T, gemm_mode);
   LFI_REQUIRE(ws_bytes >= w.bytes + gneed, LFI_ERR_WORKSPACE, "sample workspace too small: %zu < %zu", ws_bytes, w.bytes + gneed);
   void *gws = (char *)ws + w.bytes;
