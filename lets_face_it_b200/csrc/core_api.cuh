@@ -35,6 +35,7 @@ struct FwdArgs {
   float *nll;                 // [Tp][B] or nullptr
   float *z_out;               // [Tp][B][C] output of step k_last
   float *scale_out;           // [K][B][Cz] or nullptr (FlowStep.scale, models.py:336-337)
+  int *flags; size_t flags_bytes;  // progress counters of the stage-pipelined kernel (nullptr: wavefront kernels only)
 };
 
 struct InvArgs {
@@ -70,6 +71,7 @@ struct BwdArgs {
   float *dzf;                 // [K][Tp][B][C]  grad wrt 1x1 conv output (for dW)
   // small per-channel gradients accumulated with atomics, [K][.]
   float *g_an_bias, *g_an_logs, *g_b_hh, *g_bf, *g_lf;
+  int *flags; size_t flags_bytes;  // progress counters of the stage-pipelined kernel (nullptr: wavefront kernels only)
 };
 
 int fwd_smem_bytes(const Dims &d, int R);

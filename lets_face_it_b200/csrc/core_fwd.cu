@@ -9,6 +9,7 @@
 //             (SeqGlow.inference models.py:581-594 / SeqGlow.invert 617-645).
 #include "core_tile.cuh"
 #include "core_api.cuh"
+#include "core_pipe.cuh"
 #include <cstdlib>
 
 namespace lfi {
@@ -333,6 +334,7 @@ template <int RPT> static int launch_fwd_t(const FwdArgs &a, cudaStream_t st) {
 }
 
 int launch_fwd(const FwdArgs &a, cudaStream_t st) {
+  if (a.flags && !a.h0 && !a.c0 && pipe_supported(a.d, a.k_last - a.k_first + 1, false)) return launch_fwd_pipe(a, st);
   const int rpt = choose_rpt(a.d, a.B, false, false);
   switch (rpt) {
     case 8: return launch_fwd_t<8>(a, st);

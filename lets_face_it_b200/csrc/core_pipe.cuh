@@ -1,0 +1,60 @@
+// Persistent, stage-pipelined flow core (training forward / backward) for GRU coupling networks whose per-step
+// weights fit the shared memory of a 2-CTA cluster (final_model.yaml: H = 128, C = 56).
+//
+// One cluster of two CTAs owns ONE flow step k for the whole launch and keeps that step's weights (W_hh, the z1
+// columns of W_ih, LinearZeros, the 1x1 conv) and the RNN state h resident in shared memory across all frames
+// (reference: FlowStep.normal_flow models.py:311-342, f_seq.forward models.py:204-214 with the state carried on
+// the module, models.py:193-194).  The K clusters of a pipeline form a systolic chain over a tile of 64 sequences:
+// stage k evaluates frame t as soon as stage k-1 has published its output for frame t (release/acquire counter in
+// global memory), so cell (k, t) runs concurrently with (k-1, t+1), (k-2, t+2), ... - the same anti-diagonal
+// schedule as the wavefront kernels (core_fwd.cu / core_bwd.cu), without a launch per diagonal and without
+// re-streaming the weights.  Inside a cluster the hidden units are split between the two CTAs (each CTA owns 64
+// units = 192 gate columns of W_hh); the halves of h and the LinearZeros partial sums are exchanged through
+// distributed shared memory.  The recurrent product h . W_hh^T of frame t does not depend on stage k-1, so it is
+// evaluated BEFORE the stage waits for its input: only the small products sit on the stage-to-stage critical path.
+#pragma once
+#include "core_api.cuh"
+
+namespace lfi {
+namespace core {
+
+constexpr int PNT = 256;  // threads per CTA
+constexpr int PR = 64;    // sequences (rows) per cluster tile
+constexpr int PRH = 32;   // rows per CTA for the row-wise work (ActNorm, 1x1 conv, coupling)
+constexpr int PUC = 64;   // hidden units per CTA
+constexpr int PHS = 68;   // row pitch of the act-layout arrays ([reduction index][row]) over the 64 tile rows
+
+struct PipePlan {  // offsets in floats
+  int whh, wz, wf, w, vec, h, z1, xs, zrow, o, extra, total;
+  int pC, pO;
+};
+
+// forward:  whh [H][3][64] = W_hh[g*H + u][i], wz [Ci][3][64] = W_ih[g*H + u][i], wf [64][Cop] = Wf[j][u], w [C][Cp] = W
+// backward: whh [3][64][H] = W_hh[g*H + u][m], wz [3][64][Cip] = W_ih[g*H+u][i], wf [Co][64] = Wf[j][u], w [C][Cp] = W^T
+__host__ __device__ inline PipePlan plan_pipe(const Dims &d, bool bwd) {
+  PipePlan p;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += round_up(n, 4); return r; };
+  p.pC = odd(d.C);
+  p.pO = round_up(d.Co, 4) + 4;
+  p.whh = take(d.H * 3 * PUC);
+  p.wz = take((bwd ? d.Cip : d.Ci) * 3 * PUC);
+  p.wf = take(bwd ? d.Co * PUC : PUC * d.Cop);
+  p.w = take(d.C * d.Cp);
+  p.vec = take(2 * d.C + 3 * PUC + 2 * d.Co);
+  p.h = take(d.H * PHS);
+  p.z1 = take(d.Ci * PHS);
+  p.xs = take(PRH * p.pC);
+  p.zrow = take(PRH * p.pC);
+  p.o = take(2 * PRH * p.pO);
+  p.extra = 0;
+  p.total = o;
+  return p;
+}
+
+bool pipe_supported(const Dims &d, int nk, bool bwd);
+int launch_fwd_pipe(const FwdArgs &a, cudaStream_t st);
+int launch_bwd_pipe(const BwdArgs &a, cudaStream_t st);
+
+}  // namespace core
+}  // namespace lfi

@@ -93,12 +93,14 @@ static bool enc_use_planes(const lfi_shape *s, int m, size_t M, int mode) {
   return gemm_tc_wants(g);
 }
 static void *take_bf16(Bump &b, size_t n) { return (void *)b.take<uint16_t>(n); }
+constexpr size_t kFlagInts = 1024;
 struct TrainWs {
   float *cond, *Cact, *G, *ld, *gh;
   EncWs enc[LFI_NMOD];
   core::Stash st;
   // backward
   float *dx, *dh, *dc, *dG, *dAh, *dO, *dzf, *dC, *dcond, *dWcF, *xg, *dhe, *dai, *dah;
+  int *flags;  // progress counters of the stage-pipelined flow core
   size_t bytes;
 };
 
@@ -109,6 +111,7 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
   w->Cact = b.take<float>(M * K * d.D);
   w->G = b.take<float>(M * K * d.GH);
   w->ld = b.take<float>(M);
+  w->flags = b.take<int>(kFlagInts);
   size_t ghmax = 0, xgmax = 0, emax = 0;
   for (int m = 0; m < LFI_NMOD; ++m) {
     memset(&w->enc[m], 0, sizeof(EncWs));
@@ -315,6 +318,7 @@ int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params 
   a.xin = w.st.xin; a.st_y = w.st.y; a.st_zf = w.st.zf; a.st_h = w.st.h; a.st_c = w.st.c; a.st_gates = w.st.gates;
   a.st_ahn = w.st.ahn; a.st_o = w.st.o; a.ld = w.ld; a.ld_accumulate = 0; a.nll = nll; a.z_out = z;
   a.scale_out = scale_out;
+  a.flags = w.flags; a.flags_bytes = kFlagInts * sizeof(int);
   return core::launch_fwd(a, st);
 }
 
