@@ -4,6 +4,7 @@
 // dA_h (whose weight gradients are taken afterwards as time-parallel GEMMs over the stash) and the small
 // per-channel gradients (ActNorm bias/logs, b_hh, LinearZeros bias/logs) by per-CTA column sums + atomics.
 #include "core_api.cuh"
+#include "core_pipe.cuh"
 
 namespace lfi {
 namespace core {
@@ -222,6 +223,7 @@ template <int RPT> static int launch_bwd_t(const BwdArgs &a, cudaStream_t st) {
 }
 
 int launch_bwd(const BwdArgs &a, cudaStream_t st) {
+  if (a.flags && pipe_supported(a.d, a.d.K, true)) return launch_bwd_pipe(a, st);
   const int rpt = choose_rpt(a.d, a.B, true, false);
   switch (rpt) {
     case 8: return launch_bwd_t<8>(a, st);

@@ -30,16 +30,16 @@ struct PipePlan {  // offsets in floats
 };
 
 // forward:  whh [H][3][64] = W_hh[g*H + u][i], wz [Ci][3][64] = W_ih[g*H + u][i], wf [64][Cop] = Wf[j][u], w [C][Cp] = W
-// backward: whh [3][64][H] = W_hh[g*H + u][m], wz [3][64][Cip] = W_ih[g*H+u][i], wf [Co][64] = Wf[j][u], w [C][Cp] = W^T
-__host__ __device__ inline PipePlan plan_pipe(const Dims &d, bool bwd) {
+// (the backward kernel has its own plan, core_pipe_bwd.cu)
+__host__ __device__ inline PipePlan plan_pipe(const Dims &d) {
   PipePlan p;
   int o = 0;
   auto take = [&](int n) { int r = o; o += round_up(n, 4); return r; };
   p.pC = odd(d.C);
   p.pO = round_up(d.Co, 4) + 4;
   p.whh = take(d.H * 3 * PUC);
-  p.wz = take((bwd ? d.Cip : d.Ci) * 3 * PUC);
-  p.wf = take(bwd ? d.Co * PUC : PUC * d.Cop);
+  p.wz = take(d.Ci * 3 * PUC);
+  p.wf = take(PUC * d.Cop);
   p.w = take(d.C * d.Cp);
   p.vec = take(2 * d.C + 3 * PUC + 2 * d.Co);
   p.h = take(d.H * PHS);
@@ -53,6 +53,7 @@ __host__ __device__ inline PipePlan plan_pipe(const Dims &d, bool bwd) {
 }
 
 bool pipe_supported(const Dims &d, int nk, bool bwd);
+int pipe_bwd_smem_bytes(const Dims &d);
 int launch_fwd_pipe(const FwdArgs &a, cudaStream_t st);
 int launch_bwd_pipe(const BwdArgs &a, cudaStream_t st);
 

@@ -27,7 +27,7 @@ core_fwd_pipe(const FwdArgs a, const int P, const int ntiles, int *progress) {
   const int c = (int)cluster.block_rank();
   const int stage = blockIdx.y, nk = gridDim.y, k = a.k_first + stage, p = blockIdx.z;
   const int C = d.C, Ci = d.Ci, Cz = d.Cz, Co = d.Co, H = d.H, GH = d.GH, B = a.B, Tp = a.Tp, Cp = d.Cp, Cop = d.Cop;
-  const PipePlan pl = plan_pipe(d, false);
+  const PipePlan pl = plan_pipe(d);
   const int pC = pl.pC, pO = pl.pO;
   float *whh = sm + pl.whh, *wz = sm + pl.wz, *wf = sm + pl.wf, *wsm = sm + pl.w;
   float *anb = sm + pl.vec, *ans = anb + C, *bhh = ans + C, *bfs = bhh + 3 * PUC, *e3 = bfs + Co;
@@ -330,12 +330,14 @@ bool pipe_supported(const Dims &d, int nk, bool bwd) {
   if (d.C > 64 || d.Co > 64 || d.C < 2) return false;
   if (d.affine && (d.Co & 1)) return false;
   if (2 * nk > sm_count()) return false;
-  return plan_pipe(d, bwd).total * (int)sizeof(float) <= kPipeMaxSmem;
+  if (d.Ci > 32 || d.Cz > 32) return false;
+  const int bytes = bwd ? pipe_bwd_smem_bytes(d) : plan_pipe(d).total * (int)sizeof(float);
+  return bytes <= kPipeMaxSmem;
 }
 
 int launch_fwd_pipe(const FwdArgs &a, cudaStream_t st) {
   const int nk = a.k_last - a.k_first + 1;
-  const int bytes = plan_pipe(a.d, false).total * (int)sizeof(float);
+  const int bytes = plan_pipe(a.d).total * (int)sizeof(float);
   const int ntiles = (a.B + PR - 1) / PR;
   int P = sm_count() / (2 * nk);
   if (P > ntiles) P = ntiles;

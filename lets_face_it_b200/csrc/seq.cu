@@ -346,6 +346,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   a.d = d; a.dv = make_view(d, derived, p); a.B = B; a.Tp = Tp; a.dnll = dnll; a.z = z; a.st = w.st;
   a.dx = w.dx; a.dh = w.dh; a.dc = w.dc; a.dG = w.dG; a.dAh = w.dAh; a.dO = w.dO; a.dzf = w.dzf;
   a.g_an_bias = g->an_bias; a.g_an_logs = g->an_logs; a.g_b_hh = g->b_hh; a.g_bf = g->bf; a.g_lf = g->lf;
+  a.flags = w.flags; a.flags_bytes = kFlagInts * sizeof(int);
   LFI_TRY(core::launch_bwd(a, st));
 
   // 2. weight gradients of the per-step matrices as batched (over k) reductions over the M rows
