@@ -33,7 +33,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gemm", default=os.environ.get("LFI_GEMM", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--gemm", default=os.environ.get("LFI_GEMM", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
+                    help="contraction mode: bf16x3 = error-compensated split-bf16 on tcgen05 (fp32-grade, the parity mode), "
+                         "bf16 = plain bf16 operands (looser stated bound), fp32 = FFMA tiles")
+    ap.add_argument("--sample-seqs", type=int, default=1024, help="concurrent sequences per GPU of the sampling leg")
+    ap.add_argument("--sample-frames", type=int, default=750, help="generated frames per sequence (30 s at 25 fps)")
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-batch", type=int, default=32, help="sequences per step of the CPU reference arm (bounded sample)")
@@ -261,6 +265,24 @@ def run_ours(a):
     e2e = frames_step * a.steps / (ms_e2e / 1e3)
     h2d = sum(v.numel() * 4 for v in host.values())
 
+    # ---- autoregressive sampling (second half of the metric): BASELINE.json configs[3] per-GPU share -------------------
+    sample = None
+    if not a.no_sample:
+        model.eval()
+        Bs, Tg = a.sample_seqs, a.sample_frames
+        hs = make_batch(hy, Bs, START_TS + Tg, seed=5 + rank)
+        data = {k: v.to(dev) for k, v in hs.items()}
+        data["p1_face"] = torch.zeros(Bs, START_TS, hy.C, device=dev)
+        model.hparams.Infer["eps"] = 0.7
+        model.inference(START_TS + min(Tg, 32), data={k: v[:, :START_TS + min(Tg, 32)] for k, v in data.items()})
+        n0 = L.lfi_launch_count()
+        ms_s = timed(lambda: model.inference(START_TS + Tg, data=data), 1)
+        sample = {"value": Bs * Tg * world / (ms_s * 1e-3), "unit": "frames/s", "sequences_per_gpu": Bs, "frames_per_sequence": Tg, "eps": 0.7,
+                  "ms": ms_s, "gpu_launches": int(L.lfi_launch_count() - n0),
+                  "note": "SeqGlow.inference, zero seed frames, temperature 0.7, in-kernel sampler; no collective"}
+        del data, hs
+        model.train()
+
     out = {
         "metric": "train frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -273,6 +295,8 @@ def run_ours(a):
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": int(launches),
     }
+    if sample is not None:
+        out["sample"] = sample
 
     if rank == 0:
         # ---- roofline of the dominant contraction: cond_transform for all 16 steps, [B*56, 920] x [920, 8192] ---------
@@ -303,25 +327,6 @@ def run_ours(a):
                            "kernel": "cond_transform GEMM [%d x %d x %d], mode %s" % (M, N, K, a.gemm), "peak_source": how + " (burst: kernel timed alone)",
                            "step_frac_of_tensor_roofline": value / world * FLOP_PER_FRAME_TRAIN / 1e12 / sust}
         del A, W, C
-
-        # ---- autoregressive sampling throughput (secondary number of the metric) --------------------------------
-        if not a.no_sample:
-            model.eval()
-            Bs, Tg = 1024, 48
-            hs = make_batch(hy, Bs, START_TS + Tg, seed=5)
-            data = {k: v.to(dev) for k, v in hs.items()}
-            data["p1_face"] = torch.zeros(Bs, START_TS, hy.C, device=dev)
-            model.hparams.Infer["eps"] = 0.7
-            model.inference(START_TS + Tg, data=data)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            model.inference(START_TS + Tg, data=data)
-            e1.record()
-            torch.cuda.synchronize()
-            out["sample"] = {"value": Bs * Tg / (e0.elapsed_time(e1) * 1e-3), "unit": "frames/s", "sequences": Bs, "frames": Tg, "eps": 0.7,
-                             "note": "1 GPU, persistent sampler; per-frame cost is independent of the horizon"}
-            model.train()
 
         # ---- CPU baseline: the oracle port on the host cores, bounded sample -------------------------------------
         if world == 1 and not a.no_cpu_baseline:

@@ -196,8 +196,8 @@ core_fwd_pipe(const FwdArgs a, const int P, const int ntiles, int *progress) {
       for (int r = 0; r < 8; ++r)
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
-          const float rgt = sigmoidf_(ar[r][x]), ugt = sigmoidf_(au[r][x]);
-          const float ng = tanhf(ani[r][x] + rgt * anh[r][x]);
+          const float rgt = fast_sigmoid(ar[r][x]), ugt = fast_sigmoid(au[r][x]);
+          const float ng = fast_tanh(ani[r][x] + rgt * anh[r][x]);
           ar[r][x] = rgt; au[r][x] = ugt; ani[r][x] = ng;
           hreg[r][x] = ng + ugt * (hreg[r][x] - ng);
         }

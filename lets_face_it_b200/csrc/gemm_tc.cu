@@ -53,6 +53,9 @@ struct Params {
   // optional bf16 plane output of the final value (hi, and lo = bf16(v - hi) when o_lo != nullptr); C may then be null
   __nv_bfloat16 *o_hi, *o_lo; int ldo; long sO;
   int vec;  // all fp32 pointers / pitches allow 128-bit accesses
+  int fuse;     // LFI_FUSE_*
+  int cond_vec; // fused GRU forward: the cond slice allows 128-bit stores
+  GruEpi gru;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -165,6 +168,192 @@ __device__ __forceinline__ TileCoord tile_coord(const Params &p, int tile, int n
   return t;
 }
 
+
+// ---- fused encoder-GRU epilogues ---------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) { *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d); }
+__device__ __forceinline__ void st_planes4(__nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t o, const float (&v)[4]) {
+  __align__(8) __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h4[e] = __float2bfloat16_rn(v[e]);
+    l4[e] = __float2bfloat16_rn(v[e] - __bfloat162float(h4[e]));
+  }
+  *reinterpret_cast<uint2 *>(hi + o) = *reinterpret_cast<const uint2 *>(h4);
+  if (lo) *reinterpret_cast<uint2 *>(lo + o) = *reinterpret_cast<const uint2 *>(l4);
+}
+
+// One 16-column accumulator chunk: TMEM (thread = row) -> shared-memory transpose -> registers in the "coalesced"
+// arrangement of the generic epilogue: lane holds rows rr + 8i (i < 4) x columns cg .. cg+3, so that four lanes cover
+// 64 contiguous bytes of a row in every global access.
+__device__ __forceinline__ void chunk_to_rows(uint32_t taddr, float *stg, int lane, int rr, int cg, float (&x)[4][4]) {
+  uint32_t v[16];
+  tmem_ld16(taddr, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<float4 *>(&stg[lane * kEpiPitch + 4 * j]) =
+        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = *reinterpret_cast<const float4 *>(&stg[(rr + 8 * i) * kEpiPitch + cg]);
+    x[i][0] = t.x; x[i][1] = t.y; x[i][2] = t.z; x[i][3] = t.w;
+  }
+  __syncwarp();
+}
+
+// Forward (aux::enc_gate_fwd_kernel semantics): tile = 128 windows x 64 hidden units; TMEM columns [0,64) hold the r
+// pre-activations of those units, [64,128) u, [128,192) n (the B tile is gathered from the three gate blocks of W_hh).
+// Per 16-unit chunk: all global operands are requested first (they do not depend on the accumulator), then the
+// accumulator chunks are pulled out of TMEM, then gate math and stores.
+__device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t, uint32_t tbase, float *stg, int q, int half, int lane,
+                                             uint64_t *tfull, uint32_t aph) {
+  const GruEpi &G = p.gru;
+  const int E = G.E;
+  const int rr = lane & 7, cg = (lane >> 3) * 4;
+  const int u_base = (t.n0 / 192) * 64;
+  const int mrow0 = t.m0 + q * 32;
+  __nv_bfloat16 *hhi = (__nv_bfloat16 *)G.h_hi, *hlo = (__nv_bfloat16 *)G.h_lo;
+  bool waited = false;
+  for (int sc = half; sc < 4; sc += 2) {
+    const int e = min(u_base + 16 * sc + cg, E - 4);
+    float4 xr[4], xu[4], xn[4], hp[4];
+    float mk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = min(mrow0 + rr + 8 * i, p.M - 1);
+      const int b = m % G.B, tp = m / G.B;
+      const int tau = G.t0 + tp - G.hist + 1 + G.s;
+      mk[i] = G.mask ? G.mask[(size_t)m * G.hist + G.s] : 1.0f;
+      const float *xp = G.xp + ((size_t)b * G.T + tau) * 3 * E + e;
+      xr[i] = ld4(xp); xu[i] = ld4(xp + E); xn[i] = ld4(xp + 2 * E);
+      hp[i] = ld4(G.hprev + (size_t)m * E + e);
+    }
+    const float4 bir = __ldg(reinterpret_cast<const float4 *>(G.b_ih + e)), biu = __ldg(reinterpret_cast<const float4 *>(G.b_ih + E + e)),
+                 bin = __ldg(reinterpret_cast<const float4 *>(G.b_ih + 2 * E + e));
+    const float4 bhr = __ldg(reinterpret_cast<const float4 *>(G.b_hh + e)), bhu = __ldg(reinterpret_cast<const float4 *>(G.b_hh + E + e)),
+                 bhn = __ldg(reinterpret_cast<const float4 *>(G.b_hh + 2 * E + e));
+    if (!waited) { mbar_wait(tfull, aph); tc_fence_after(); waited = true; }
+    float ar[4][4], au[4][4], an[4][4];
+    chunk_to_rows(tbase + sc * 16, stg, lane, rr, cg, ar);
+    chunk_to_rows(tbase + 64 + sc * 16, stg, lane, rr, cg, au);
+    chunk_to_rows(tbase + 128 + sc * 16, stg, lane, rr, cg, an);
+    if (u_base + 16 * sc + cg >= E) continue;
+    const float bir_[4] = {bir.x, bir.y, bir.z, bir.w}, biu_[4] = {biu.x, biu.y, biu.z, biu.w}, bin_[4] = {bin.x, bin.y, bin.z, bin.w};
+    const float bhr_[4] = {bhr.x, bhr.y, bhr.z, bhr.w}, bhu_[4] = {bhu.x, bhu.y, bhu.z, bhu.w}, bhn_[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = mrow0 + rr + 8 * i;
+      if (m < p.M) {
+        const float xr_[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w}, xu_[4] = {xu[i].x, xu[i].y, xu[i].z, xu[i].w};
+        const float xn_[4] = {xn[i].x, xn[i].y, xn[i].z, xn[i].w}, hp_[4] = {hp[i].x, hp[i].y, hp[i].z, hp[i].w};
+        float rg[4], ug[4], ng[4], ah[4], hn[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float air = mk[i] * xr_[c] + bir_[c], aiu = mk[i] * xu_[c] + biu_[c], ain = mk[i] * xn_[c] + bin_[c];
+          const float ahr = bhr_[c] + ar[i][c], ahu = bhu_[c] + au[i][c];
+          ah[c] = bhn_[c] + an[i][c];
+          rg[c] = fast_sigmoid(air + ahr);
+          ug[c] = fast_sigmoid(aiu + ahu);
+          ng[c] = fast_tanh(ain + rg[c] * ah[c]);
+          hn[c] = ng[c] + ug[c] * (hp_[c] - ng[c]);
+        }
+        const size_t o1 = (size_t)m * E + e, o3 = (size_t)m * 3 * E + e;
+        st4(G.h + o1, hn[0], hn[1], hn[2], hn[3]);
+        if (G.gates) {
+          st4(G.gates + o3, rg[0], rg[1], rg[2], rg[3]);
+          st4(G.gates + o3 + E, ug[0], ug[1], ug[2], ug[3]);
+          st4(G.gates + o3 + 2 * E, ng[0], ng[1], ng[2], ng[3]);
+        }
+        if (G.ahn) st4(G.ahn + o1, ah[0], ah[1], ah[2], ah[3]);
+        if (G.cond) {
+          float *cd = G.cond + (size_t)m * G.cond_ld + e;
+          if (p.cond_vec) st4(cd, hn[0], hn[1], hn[2], hn[3]);
+          else { cd[0] = hn[0]; cd[1] = hn[1]; cd[2] = hn[2]; cd[3] = hn[3]; }
+        }
+        if (hhi) st_planes4(hhi, hlo, o1, hn);
+      }
+    }
+  }
+  if (!waited) { mbar_wait(tfull, aph); tc_fence_after(); }
+}
+
+// Backward (aux::enc_gate_bwd2_kernel semantics): the accumulator tile is dA_h(s) W_hh for 128 windows x all E units;
+// dh_{s-1} = tile + dh (direct part), then the gate backward of step s-1.  Bias gradients: per-lane sums over its four
+// rows, butterfly over the eight row lanes, one atomic per column and warp.
+__device__ __forceinline__ void gru_bwd_tile(const Params &p, const TileCoord &t, uint32_t tbase, float *stg, int q, int half, int lane,
+                                             uint64_t *tfull, uint32_t aph) {
+  const GruEpi &G = p.gru;
+  const int E = G.E;
+  const int rr = lane & 7, cg = (lane >> 3) * 4;
+  const int mrow0 = t.m0 + q * 32;
+  __nv_bfloat16 *dah_hi = (__nv_bfloat16 *)G.dah_hi, *dah_lo = (__nv_bfloat16 *)G.dah_lo;
+  __nv_bfloat16 *dan_hi = (__nv_bfloat16 *)G.dan_hi, *dan_lo = (__nv_bfloat16 *)G.dan_lo;
+  bool waited = false;
+  for (int sc = half; sc < E / 16; sc += 2) {
+    const int e = 16 * sc + cg;
+    float4 d4[4], r4[4], u4[4], n4[4], a4[4], h4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = min(mrow0 + rr + 8 * i, p.M - 1);
+      const size_t o1 = (size_t)m * E + e, o3 = (size_t)m * 3 * E + e;
+      d4[i] = ld4(G.dh + o1); r4[i] = ld4(G.bgates + o3); u4[i] = ld4(G.bgates + o3 + E); n4[i] = ld4(G.bgates + o3 + 2 * E);
+      a4[i] = ld4(G.bahn + o1);
+      h4[i] = G.bhprev ? ld4(G.bhprev + o1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (!waited) { mbar_wait(tfull, aph); tc_fence_after(); waited = true; }
+    float acc[4][4];
+    chunk_to_rows(tbase + sc * 16, stg, lane, rr, cg, acc);
+    float s_r[4] = {0.f, 0.f, 0.f, 0.f}, s_u[4] = {0.f, 0.f, 0.f, 0.f}, s_n[4] = {0.f, 0.f, 0.f, 0.f}, s_nr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = mrow0 + rr + 8 * i;
+      if (m < p.M) {
+        const size_t o1 = (size_t)m * E + e, o3 = (size_t)m * 3 * E + e;
+        const float dd[4] = {d4[i].x, d4[i].y, d4[i].z, d4[i].w}, rg[4] = {r4[i].x, r4[i].y, r4[i].z, r4[i].w}, uu[4] = {u4[i].x, u4[i].y, u4[i].z, u4[i].w};
+        const float nn[4] = {n4[i].x, n4[i].y, n4[i].z, n4[i].w}, aa[4] = {a4[i].x, a4[i].y, a4[i].z, a4[i].w}, hh[4] = {h4[i].x, h4[i].y, h4[i].z, h4[i].w};
+        float dar[4], dau[4], dan[4], dnr[4], dhn[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float dh = dd[c] + acc[i][c];
+          const float dn = dh * (1.0f - uu[c]), du = dh * (hh[c] - nn[c]);
+          dan[c] = dn * (1.0f - nn[c] * nn[c]);
+          dau[c] = du * uu[c] * (1.0f - uu[c]);
+          dar[c] = dan[c] * aa[c] * rg[c] * (1.0f - rg[c]);
+          dnr[c] = dan[c] * rg[c];
+          dhn[c] = dh * uu[c];
+          s_r[c] += dar[c]; s_u[c] += dau[c]; s_n[c] += dan[c]; s_nr[c] += dnr[c];
+        }
+        st4(G.dh + o1, dhn[0], dhn[1], dhn[2], dhn[3]);
+        st_planes4(dah_hi, dah_lo, o3, dar);
+        st_planes4(dah_hi, dah_lo, o3 + E, dau);
+        st_planes4(dah_hi, dah_lo, o3 + 2 * E, dnr);
+        st_planes4(dan_hi, dan_lo, o1, dan);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        s_r[c] += __shfl_xor_sync(0xffffffffu, s_r[c], o);
+        s_u[c] += __shfl_xor_sync(0xffffffffu, s_u[c], o);
+        s_n[c] += __shfl_xor_sync(0xffffffffu, s_n[c], o);
+        s_nr[c] += __shfl_xor_sync(0xffffffffu, s_nr[c], o);
+      }
+    }
+    if (rr == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        atomicAdd(G.gb_ih + e + c, s_r[c]); atomicAdd(G.gb_ih + E + e + c, s_u[c]); atomicAdd(G.gb_ih + 2 * E + e + c, s_n[c]);
+        atomicAdd(G.gb_hh + e + c, s_r[c]); atomicAdd(G.gb_hh + E + e + c, s_u[c]); atomicAdd(G.gb_hh + 2 * E + e + c, s_nr[c]);
+      }
+    }
+  }
+  if (!waited) { mbar_wait(tfull, aph); tc_fence_after(); }
+}
+
+template <int FUSE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1) {
@@ -216,7 +405,11 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
             } else {
               for (int j = 0; j < BM / 64; ++j) tma_load_3d(sa + pl * a_plane + j * (BK * 128), ma, &full[s], t.m0 + 64 * j, k0, t.b);
             }
-            if (!p.b_mn) {
+            if (FUSE == LFI_FUSE_GRU_FWD) {
+              // 64 hidden units x (r, u, n): three 64-row boxes of W_hh, 8-row swizzle atoms stay contiguous
+              const int u0 = (t.n0 / 192) * 64;
+              for (int g = 0; g < 3; ++g) tma_load_3d(sb + pl * b_plane + g * (64 * 128), mb, &full[s], k0, g * p.gru.E + u0, t.b);
+            } else if (!p.b_mn) {
               tma_load_3d(sb + pl * b_plane, mb, &full[s], k0, t.n0, t.b);
             } else {
               for (int j = 0; j < p.bn / 64; ++j) tma_load_3d(sb + pl * b_plane + j * (BK * 128), mb, &full[s], t.n0 + 64 * j, k0, t.b);
@@ -288,7 +481,13 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
       const bool has_work = t.kb1 > t.kb0;
       const int mrow0 = t.m0 + q * 32;
       bool waited = false;
-      for (int sc = half; sc < p.bn / 16; sc += 2) {
+      if constexpr (FUSE != LFI_FUSE_NONE) {
+        const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+        if constexpr (FUSE == LFI_FUSE_GRU_FWD) gru_fwd_tile(p, t, tb, stg, q, half, lane, &tfull[as], aph);
+        else gru_bwd_tile(p, t, tb, stg, q, half, lane, &tfull[as], aph);
+        waited = true;
+      }
+      for (int sc = half; sc < p.bn / 16 && FUSE == LFI_FUSE_NONE; sc += 2) {
         const int nc0 = t.n0 + sc * 16;
         if (nc0 >= p.N) break;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + sc * 16;
@@ -487,6 +686,17 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   memset(&p, 0, sizeof(p));
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
   p.bn = choose_bn(g.N);
+  p.fuse = g.fuse; p.gru = g.gru;
+  if (g.fuse == LFI_FUSE_GRU_FWD) {
+    LFI_REQUIRE(g.gru.E % 64 == 0 && g.N == 3 * g.gru.E && !B.mn && g.batch == 1, LFI_ERR_SHAPE, "gemm_tc: fused GRU forward needs E %% 64 == 0");
+    p.bn = 192;
+    const float *cd = g.gru.cond;
+    p.cond_vec = cd && (((uintptr_t)cd & 15) == 0) && g.gru.cond_ld % 4 == 0;
+  } else if (g.fuse == LFI_FUSE_GRU_BWD) {
+    LFI_REQUIRE(g.gru.E == g.N && (g.N == 64 || g.N == 128 || g.N == 192 || g.N == 256) && g.batch == 1, LFI_ERR_SHAPE,
+                "gemm_tc: fused GRU backward needs E in {64,128,192,256}");
+    p.bn = g.N;
+  }
   p.nplanes = nplanes; p.a_mn = A.mn; p.b_mn = B.mn;
   p.tiles_m = (g.M + BM - 1) / BM; p.tiles_n = (g.N + p.bn - 1) / p.bn;
   const int stage_bytes = nplanes * (BM * BK * 2 + p.bn * BK * 2);
@@ -522,7 +732,7 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   if (g.pOut.hi) p.vec = p.vec && al16(g.pOut.hi) && (!g.pOut.lo || al16(g.pOut.lo)) && g.pOut.ld % 4 == 0 && g.pOut.stride % 4 == 0;
 
   CUtensorMap mA0, mA1, mB0, mB1;
-  const int a_box = A.mn ? BK : BM, b_box = B.mn ? BK : p.bn;
+  const int a_box = A.mn ? BK : BM, b_box = B.mn ? BK : (g.fuse == LFI_FUSE_GRU_FWD ? 64 : p.bn);
   LFI_TRY(make_map(&mA0, A.hi, A.rows, A.cols, A.ldp, A.stride, g.batch, a_box));
   LFI_TRY(make_map(&mB0, B.hi, B.rows, B.cols, B.ldp, B.stride, g.batch, b_box));
   if (nplanes == 2) {
@@ -534,14 +744,18 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   const int smem = p.stages * stage_bytes + fixed;
   static bool attr_set = false;
   if (!attr_set) {
-    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_GRU_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_GRU_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
   const long ntiles = tiles * p.splitk;
   const int grid = (int)(ntiles < g_sms ? ntiles : g_sms);
   // request > half of the SM's shared memory so that two CTAs (each wanting all 512 TMEM columns) never share an SM
   const int smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;
-  gemm_tc_kernel<<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
+  if (g.fuse == LFI_FUSE_GRU_FWD) gemm_tc_kernel<LFI_FUSE_GRU_FWD><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
+  else if (g.fuse == LFI_FUSE_GRU_BWD) gemm_tc_kernel<LFI_FUSE_GRU_BWD><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
+  else gemm_tc_kernel<LFI_FUSE_NONE><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
   LFI_LAUNCH_CHECK();
   return LFI_OK;
 }
@@ -584,7 +798,7 @@ int gemm_tc(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t
   const size_t need = tc::split_ws_bytes(g, nplanes);
   LFI_REQUIRE((g.pA.hi && g.pB.hi) || (ws && ws_bytes >= need), LFI_ERR_WORKSPACE,
               "gemm_tc: operand-plane workspace too small (%zu < %zu) for %dx%dx%d b=%d", ws_bytes, need, g.M, g.N, g.K, g.batch);
-  LFI_REQUIRE((g.A || g.pA.hi) && (g.B || g.pB.hi) && (g.C || g.pOut.hi), LFI_ERR_ARG, "gemm: null operand");
+  LFI_REQUIRE((g.A || g.pA.hi) && (g.B || g.pB.hi) && (g.C || g.pOut.hi || g.fuse), LFI_ERR_ARG, "gemm: null operand");
   LFI_REQUIRE(nplanes == 1 || ((!g.pA.hi || g.pA.lo) && (!g.pB.hi || g.pB.lo)), LFI_ERR_ARG, "gemm: split-bf16 mode needs lo planes");
   LFI_REQUIRE(!(g.epi & LFI_EPI_BIAS) || g.bias, LFI_ERR_ARG, "gemm: bias epilogue without bias");
   LFI_REQUIRE(!(g.epi & LFI_EPI_LRELU_BWD) || g.aux, LFI_ERR_ARG, "gemm: lrelu-bwd epilogue without aux");

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/lfi_b200.h"
@@ -56,6 +57,14 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
 __host__ __device__ inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// MUFU-based variants for the fused hot loops (ex2.approx + rcp.approx: ~1e-6 relative, far inside the 1e-4 parity bound)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+inline bool env_flag(const char *name, bool dflt) {
+  const char *e = getenv(name);
+  return e ? (e[0] != '0') : dflt;
+}
 
 // ---- derived shape facts -----------------------------------------------------------------------
 struct Dims {
@@ -124,6 +133,23 @@ struct PlaneRef {
   int ld; long stride;
 };
 
+// Fused encoder-GRU epilogues of the tcgen05 GEMM (ModalityEncoder nn.GRU, models.py:21-27, 63-64): the window step's
+// recurrent product h_{s-1} W_hh^T (forward) / dA_h W_hh (backward) leaves TMEM straight into the gate math, so the
+// [M, 3E] pre-activation matrix never travels through HBM.  Argument meaning as aux::EncStep / aux::EncStepBwd2.
+enum { LFI_FUSE_NONE = 0, LFI_FUSE_GRU_FWD = 1, LFI_FUSE_GRU_BWD = 2 };
+struct GruEpi {
+  int E, s, hist, B, T, t0;
+  // forward (step s >= 1)
+  const float *xp, *b_ih, *b_hh, *mask, *hprev;
+  float *h, *gates, *ahn, *cond; int cond_ld;
+  void *h_hi, *h_lo;
+  // backward: the GEMM of step s yields dh_{s-1}; the epilogue runs the gate backward of step s-1
+  const float *bgates, *bahn, *bhprev;   // stash of step s-1 (bhprev = h_{s-2}, nullptr when s-1 == 0)
+  float *dh;                             // [M][E] in: direct part dh_s * u_s, out: dh_{s-1} * u_{s-1}
+  void *dah_hi, *dah_lo, *dan_hi, *dan_lo;
+  float *gb_ih, *gb_hh;
+};
+
 struct GemmArgs {
   int transA, transB, M, N, K;
   const float *A; int lda; long sA;
@@ -134,6 +160,8 @@ struct GemmArgs {
   int batch, epi;
   PlaneRef pA, pB;  // hi != nullptr: operand already split (A / B may then be null); tensor-core modes only
   PlaneRef pOut;    // hi != nullptr: also emit the result as bf16 planes (C may then be null); tensor-core modes only
+  int fuse;         // LFI_FUSE_*: replaces the generic epilogue (operands must be planes; tensor-core modes only)
+  GruEpi gru;
 };
 int gemm_simt(const GemmArgs &g, cudaStream_t st);
 int gemm_dispatch(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st);

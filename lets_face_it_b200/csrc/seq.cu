@@ -8,6 +8,7 @@
 // gemm_dispatch; the sequential recurrences go through the flow-core kernels.
 #include "aux_kernels.cuh"
 #include "core_api.cuh"
+#include <cstdlib>
 
 namespace lfi {
 
@@ -199,7 +200,8 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
       const int cur = stash ? sidx : (sidx & 1), prv = stash ? sidx - 1 : ((sidx - 1) & 1);
       hcur = ew.hs + (size_t)cur * M * E;
       if (sidx) hprev = ew.hs + (size_t)prv * M * E;
-      if (sidx) {
+      const bool fused = sidx && ew.planes && E % 64 == 0 && env_flag("LFI_FUSED_GRU_FWD", true);
+      if (sidx && !fused) {
         GemmArgs gg = gemm_args(0, 1, (int)M, 3 * E, E, hprev, E, p->enc_w_hh[m], E, gh, 3 * E);
         if (ew.planes) {
           gg.pA = plane_ref((uint16_t *)ew.hp_hi + (size_t)prv * M * E, lo ? (uint16_t *)ew.hp_lo + (size_t)prv * M * E : nullptr, E);
@@ -216,6 +218,19 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
       a.h_hi = ew.planes ? (void *)((uint16_t *)ew.hp_hi + (size_t)cur * M * E) : nullptr;
       a.h_lo = (ew.planes && lo) ? (void *)((uint16_t *)ew.hp_lo + (size_t)cur * M * E) : nullptr;
       a.s = sidx; a.hist = hist; a.B = B; a.T = T; a.Tp = Tp; a.t0 = t0; a.E = E;
+      if (fused) {
+        // recurrent product and gate math in one launch: the [M, 3E] pre-activations stay in TMEM
+        GemmArgs gg = gemm_args(0, 1, (int)M, 3 * E, E, nullptr, E, nullptr, E, nullptr, 3 * E);
+        gg.pA = plane_ref((uint16_t *)ew.hp_hi + (size_t)prv * M * E, lo ? (uint16_t *)ew.hp_lo + (size_t)prv * M * E : nullptr, E);
+        gg.pB = plane_ref(ew.whh_hi, ew.whh_lo, E);
+        gg.fuse = LFI_FUSE_GRU_FWD;
+        GruEpi &q = gg.gru;
+        q.E = E; q.s = sidx; q.hist = hist; q.B = B; q.T = T; q.t0 = t0;
+        q.xp = a.xp; q.b_ih = a.b_ih; q.b_hh = a.b_hh; q.mask = a.mask; q.hprev = a.hprev;
+        q.h = a.h; q.gates = a.gates; q.ahn = a.ahn; q.cond = a.cond; q.cond_ld = a.cond_ld; q.h_hi = a.h_hi; q.h_lo = a.h_lo;
+        LFI_TRY(gemm_dispatch(mode, gg, gws, gws_bytes, st));
+        continue;
+      }
       LFI_TRY(aux::enc_gate_fwd(a, st));
     }
   }
@@ -398,6 +413,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
     if (ew.planes) LFI_TRY(split_to_planes(w.xg, (int)(hist * M), dim, dim, 0, 1, ew.xg_hi, lo ? ew.xg_lo : nullptr, st));
     LFI_TRY(aux::fill(w.dhe, 0.f, M * E, st));
     auto off16 = [](void *base, size_t n) -> void * { return base ? (void *)((uint16_t *)base + n) : nullptr; };
+    const bool fused = ew.planes && (E == 64 || E == 128 || E == 192 || E == 256) && env_flag("LFI_FUSED_GRU_BWD", false);
     for (int sidx = hist - 1; sidx >= 0; --sidx) {
       aux::EncStepBwd2 e;
       memset(&e, 0, sizeof(e));
@@ -411,10 +427,21 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
         e.dah32 = ew.dah32 + (size_t)sidx * M * 3 * E; e.dan32 = ew.dan32 + (size_t)sidx * M * E;
       }
       e.gb_ih = g->enc_b_ih[m]; e.gb_hh = g->enc_b_hh[m]; e.M = (int)M; e.E = E;
-      LFI_TRY(aux::enc_gate_bwd2(e, st));
+      if (!fused || sidx == hist - 1) LFI_TRY(aux::enc_gate_bwd2(e, st));
       if (sidx) {  // dh_{s-1} += dA_h W_hh
         GemmArgs t = gemm_args(0, 0, (int)M, E, 3 * E, e.dah32, 3 * E, p->enc_w_hh[m], E, w.dhe, E, LFI_EPI_ACCUM);
         if (ew.planes) { t.pA = plane_ref(e.dah_hi, e.dah_lo, 3 * E); t.pB = plane_ref(ew.whh_hi, ew.whh_lo, E); }
+        if (fused) {  // ... and the gate backward of step s-1 in the same launch
+          t.C = nullptr; t.epi = 0; t.fuse = LFI_FUSE_GRU_BWD;
+          GruEpi &q = t.gru;
+          q.E = E;
+          q.bgates = ew.gates + (size_t)(sidx - 1) * M * 3 * E; q.bahn = ew.ahn + (size_t)(sidx - 1) * M * E;
+          q.bhprev = sidx - 1 > 0 ? ew.hs + (size_t)(sidx - 2) * M * E : nullptr;
+          q.dh = w.dhe;
+          q.dah_hi = off16(ew.dah_hi, (size_t)(sidx - 1) * M * 3 * E); q.dah_lo = lo ? off16(ew.dah_lo, (size_t)(sidx - 1) * M * 3 * E) : nullptr;
+          q.dan_hi = off16(ew.dan_hi, (size_t)(sidx - 1) * M * E);     q.dan_lo = lo ? off16(ew.dan_lo, (size_t)(sidx - 1) * M * E) : nullptr;
+          q.gb_ih = g->enc_b_ih[m]; q.gb_hh = g->enc_b_hh[m];
+        }
         LFI_TRY(gemm_dispatch(gemm_mode, t, gws, gws_bytes, st));
       }
     }
