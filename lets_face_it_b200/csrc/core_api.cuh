@@ -36,6 +36,9 @@ struct FwdArgs {
   float *z_out;               // [Tp][B][C] output of step k_last
   float *scale_out;           // [K][B][Cz] or nullptr (FlowStep.scale, models.py:336-337)
   int *flags; size_t flags_bytes;  // progress counters of the stage-pipelined kernel (nullptr: wavefront kernels only)
+  // tensor-core modes, stage-pipelined kernel only: bf16 operand planes (hi, lo = bf16(v - hi); lo nullable) of the stash
+  // entries the weight-gradient GEMMs contract over, written next to the fp32 stash
+  void *py_hi, *py_lo, *pzf_hi, *pzf_lo, *ph_hi, *ph_lo;
 };
 
 struct InvArgs {
@@ -72,6 +75,10 @@ struct BwdArgs {
   // small per-channel gradients accumulated with atomics, [K][.]
   float *g_an_bias, *g_an_logs, *g_b_hh, *g_bf, *g_lf;
   int *flags; size_t flags_bytes;  // progress counters of the stage-pipelined kernel (nullptr: wavefront kernels only)
+  // tensor-core modes, stage-pipelined kernel only: the gate / LinearZeros / 1x1-conv gradients leave the kernel as bf16
+  // operand planes (same geometry as dG / dAh / dO / dzf, which may then be nullptr) and b_ih is reduced in-kernel
+  void *pdG_hi, *pdG_lo, *pdAh_hi, *pdAh_lo, *pdO_hi, *pdO_lo, *pdzf_hi, *pdzf_lo;
+  float *g_b_ih;
 };
 
 int fwd_smem_bytes(const Dims &d, int R);

@@ -14,6 +14,7 @@
 // evaluated BEFORE the stage waits for its input: only the small products sit on the stage-to-stage critical path.
 #pragma once
 #include "core_api.cuh"
+#include <cuda_bf16.h>
 
 namespace lfi {
 namespace core {
@@ -50,6 +51,18 @@ __host__ __device__ inline PipePlan plan_pipe(const Dims &d) {
   p.extra = 0;
   p.total = o;
   return p;
+}
+
+// fp32 -> split-bf16 operand planes (gemm_tc.cu): hi = bf16(v), lo = bf16(v - hi)
+__device__ __forceinline__ void put_plane(void *hi, void *lo, size_t idx, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  ((__nv_bfloat16 *)hi)[idx] = h;
+  if (lo) ((__nv_bfloat16 *)lo)[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ void put_plane2(void *hi, void *lo, size_t idx, float v0, float v1) {  // idx even
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  *reinterpret_cast<__nv_bfloat162 *>((__nv_bfloat16 *)hi + idx) = h;
+  if (lo) *reinterpret_cast<__nv_bfloat162 *>((__nv_bfloat16 *)lo + idx) = __floats2bfloat162_rn(v0 - __low2float(h), v1 - __high2float(h));
 }
 
 bool pipe_supported(const Dims &d, int nk, bool bwd);

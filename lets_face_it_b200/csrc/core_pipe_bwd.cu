@@ -100,7 +100,7 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
   int it = 0;
 
   // per-channel gradient accumulators (flushed once at the end)
-  float gbhh[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  float gbhh[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, gbin[2] = {0.f, 0.f};
   float gbf[2] = {0.f, 0.f}, glf[2] = {0.f, 0.f};
   float gab[4] = {0.f, 0.f, 0.f, 0.f}, gal[4] = {0.f, 0.f, 0.f, 0.f};
 
@@ -184,7 +184,12 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
         dlin[j * PHS + lr0 + r] = v;
         peer[pl.dact + PUC * PHS + j * PHS + lr0 + r] = v;
       }
-      for (int e = tid; e < nmy * Co; e += PNT) { const int r = e / Co, j = e - r * Co; a.dO[(cell * B + row0 + lr0 + r) * Co + j] = dor[r * pO + j]; }
+      for (int e = tid; e < nmy * Co; e += PNT) {
+        const int r = e / Co, j = e - r * Co;
+        const size_t o = (cell * B + row0 + lr0 + r) * Co + j;
+        if (a.dO) a.dO[o] = dor[r * pO + j];
+        if (a.pdO_hi) put_plane(a.pdO_hi, a.pdO_lo, o, dor[r * pO + j]);
+      }
       cluster.sync();  // X1: dlin of all 64 rows present in both CTAs
 
       // ---- 3. dh = dlin @ Wf (+ carried gradient) for this thread's rows x units ---------------------------------------
@@ -216,7 +221,7 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
           dar[r][x] = v_an * an * rgt * (1.0f - rgt);
           dnr[r][x] = v_an * rgt;
           carry[r][x] = g * ug;
-          gbhh[0][x] += dar[r][x]; gbhh[1][x] += dau[r][x]; gbhh[2][x] += dnr[r][x];
+          gbhh[0][x] += dar[r][x]; gbhh[1][x] += dau[r][x]; gbhh[2][x] += dnr[r][x]; gbin[x] += v_an;
         }
       {  // dA_i -> dG (time-parallel backward), dA_h stash (dW_hh)
         const size_t ldg = (size_t)K * GH;
@@ -224,14 +229,29 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
         for (int r = 0; r < 8; ++r) {
           if (8 * rg + r < nrows) {
             const int b = row0 + 8 * rg + r;
-            float *gq = a.dG + ((size_t)t * B + b) * ldg + (size_t)k * GH + uo;
-            float *hq = a.dAh + (cell * B + b) * GH + uo;
-            *reinterpret_cast<float2 *>(gq) = make_float2(dar[r][0], dar[r][1]);
-            *reinterpret_cast<float2 *>(gq + H) = make_float2(dau[r][0], dau[r][1]);
-            *reinterpret_cast<float2 *>(gq + 2 * H) = make_float2(dan[r][0], dan[r][1]);
-            *reinterpret_cast<float2 *>(hq) = make_float2(dar[r][0], dar[r][1]);
-            *reinterpret_cast<float2 *>(hq + H) = make_float2(dau[r][0], dau[r][1]);
-            *reinterpret_cast<float2 *>(hq + 2 * H) = make_float2(dnr[r][0], dnr[r][1]);
+            const size_t go = ((size_t)t * B + b) * ldg + (size_t)k * GH + uo, ho = (cell * B + b) * GH + uo;
+            if (a.dG) {
+              float *gq = a.dG + go;
+              *reinterpret_cast<float2 *>(gq) = make_float2(dar[r][0], dar[r][1]);
+              *reinterpret_cast<float2 *>(gq + H) = make_float2(dau[r][0], dau[r][1]);
+              *reinterpret_cast<float2 *>(gq + 2 * H) = make_float2(dan[r][0], dan[r][1]);
+            }
+            if (a.dAh) {
+              float *hq = a.dAh + ho;
+              *reinterpret_cast<float2 *>(hq) = make_float2(dar[r][0], dar[r][1]);
+              *reinterpret_cast<float2 *>(hq + H) = make_float2(dau[r][0], dau[r][1]);
+              *reinterpret_cast<float2 *>(hq + 2 * H) = make_float2(dnr[r][0], dnr[r][1]);
+            }
+            if (a.pdG_hi) {
+              put_plane2(a.pdG_hi, a.pdG_lo, go, dar[r][0], dar[r][1]);
+              put_plane2(a.pdG_hi, a.pdG_lo, go + H, dau[r][0], dau[r][1]);
+              put_plane2(a.pdG_hi, a.pdG_lo, go + 2 * H, dan[r][0], dan[r][1]);
+            }
+            if (a.pdAh_hi) {
+              put_plane2(a.pdAh_hi, a.pdAh_lo, ho, dar[r][0], dar[r][1]);
+              put_plane2(a.pdAh_hi, a.pdAh_lo, ho + H, dau[r][0], dau[r][1]);
+              put_plane2(a.pdAh_hi, a.pdAh_lo, ho + 2 * H, dnr[r][0], dnr[r][1]);
+            }
           }
         }
       }
@@ -316,7 +336,12 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
         dzf[r * pC + i] += dz1[r * PZ1 + i] + dz1[PRH * PZ1 + r * PZ1 + i];
       }
       __syncthreads();
-      for (int e = tid; e < nmy * C; e += PNT) { const int r = e / C, j = e - r * C; a.dzf[(cell * B + row0 + lr0 + r) * C + j] = dzf[r * pC + j]; }
+      for (int e = tid; e < nmy * C; e += PNT) {
+        const int r = e / C, j = e - r * C;
+        const size_t o = (cell * B + row0 + lr0 + r) * C + j;
+        if (a.dzf) a.dzf[o] = dzf[r * pC + j];
+        if (a.pdzf_hi) put_plane(a.pdzf_hi, a.pdzf_lo, o, dzf[r * pC + j]);
+      }
       if (kact) {
         float dy[2][4];
 #pragma unroll
@@ -358,7 +383,10 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
 #pragma unroll
   for (int g = 0; g < 3; ++g)
 #pragma unroll
-    for (int x = 0; x < 2; ++x) atomicAdd(&a.g_b_hh[(size_t)k * GH + g * H + uo + x], gbhh[g][x]);
+    for (int x = 0; x < 2; ++x) {
+      atomicAdd(&a.g_b_hh[(size_t)k * GH + g * H + uo + x], gbhh[g][x]);
+      if (a.g_b_ih) atomicAdd(&a.g_b_ih[(size_t)k * GH + g * H + uo + x], g == 2 ? gbin[x] : gbhh[g][x]);
+    }
   if (lane < Cz) {
     if (d.affine) {
       atomicAdd(&a.g_bf[(size_t)k * Co + 2 * lane], gbf[0] * e3[2 * lane]);

@@ -130,6 +130,7 @@ core_fwd_pipe(const FwdArgs a, const int P, const int ntiles, int *progress) {
           const float x = first ? a.x0[(size_t)b * a.x_sb + (size_t)t * a.x_st + cc] : __ldcg(a.xin + (cell * B + b) * C + cc);
           v = (x + anb[cc]) * ans[cc];
           if (a.st_y) a.st_y[(cell * B + b) * C + cc] = v;
+          if (a.py_hi) put_plane(a.py_hi, a.py_lo, (cell * B + b) * C + cc, v);
         }
         xs[r * pC + cc] = v;
       }
@@ -167,7 +168,12 @@ core_fwd_pipe(const FwdArgs a, const int P, const int ntiles, int *progress) {
         peer[pl.z1 + j * PHS + lr0 + r] = v;
       }
       if (a.st_zf)
-        for (int e = tid; e < nmy * C; e += PNT) { const int r = e / C, j = e - r * C; a.st_zf[(cell * B + row0 + lr0 + r) * C + j] = zrow[r * pC + j]; }
+        for (int e = tid; e < nmy * C; e += PNT) {
+          const int r = e / C, j = e - r * C;
+          const size_t o = (cell * B + row0 + lr0 + r) * C + j;
+          a.st_zf[o] = zrow[r * pC + j];
+          if (a.pzf_hi) put_plane(a.pzf_hi, a.pzf_lo, o, zrow[r * pC + j]);
+        }
       cluster.sync();  // A: z1 complete in both CTAs; both are done reading h of the previous frame
 
       // ---- 3. z1 part of the gate-ih product, GRU gate math (torch nn.GRUCell, gate order r, z, n) ------------------
@@ -215,6 +221,7 @@ core_fwd_pipe(const FwdArgs a, const int P, const int ntiles, int *progress) {
             }
             if (a.st_ahn) *reinterpret_cast<float2 *>(a.st_ahn + (rb + r) * H + uo) = make_float2(anh[r][0], anh[r][1]);
             *reinterpret_cast<float2 *>(a.st_h + (rb + r) * H + uo) = make_float2(hreg[r][0], hreg[r][1]);
+            if (a.ph_hi) put_plane2(a.ph_hi, a.ph_lo, (rb + r) * H + uo, hreg[r][0], hreg[r][1]);
           }
         }
       }

@@ -8,6 +8,7 @@
 // gemm_dispatch; the sequential recurrences go through the flow-core kernels.
 #include "aux_kernels.cuh"
 #include "core_api.cuh"
+#include "core_pipe.cuh"
 #include <cstdlib>
 
 namespace lfi {
@@ -102,8 +103,19 @@ struct TrainWs {
   // backward
   float *dx, *dh, *dc, *dG, *dAh, *dO, *dzf, *dC, *dcond, *dWcF, *xg, *dhe, *dai, *dah;
   int *flags;  // progress counters of the stage-pipelined flow core
+  // tensor-core modes with the stage-pipelined core: GEMM operands of the flow-step contractions live as bf16 planes
+  // written by their producers (GEMM epilogues, core kernels), never re-split
+  bool cp, cp_lo;
+  void *cact_hi, *cact_lo, *y_hi, *y_lo, *zf_hi, *zf_lo, *h_hi, *h_lo;
+  void *dG_hi, *dG_lo, *dAh_hi, *dAh_lo, *dO_hi, *dO_lo, *dzf_hi, *dzf_lo, *dC_hi, *dC_lo;
   size_t bytes;
 };
+
+static bool core_planes_ok(const Dims &d, int mode) {
+  if (mode == LFI_GEMM_FP32 || !env_flag("LFI_CORE_PLANES", true)) return false;
+  if (!core::pipe_supported(d, d.K, false) || !core::pipe_supported(d, d.K, true)) return false;
+  return d.C % 8 == 0 && d.Co % 8 == 0 && d.H % 8 == 0 && d.D % 8 == 0;
+}
 
 static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode, void *ws, TrainWs *w) {
   Bump b(ws, 0);
@@ -164,6 +176,15 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
   w->xg = b.take<float>(xgmax);
   w->dhe = b.take<float>(M * emax);
   w->dai = nullptr; w->dah = nullptr;
+  w->cp = core_planes_ok(d, mode); w->cp_lo = mode == LFI_GEMM_BF16X3;
+  if (w->cp) {
+    auto two = [&](void *&hi, void *&lo_, size_t n) { hi = take_bf16(b, n); lo_ = w->cp_lo ? take_bf16(b, n) : nullptr; };
+    two(w->cact_hi, w->cact_lo, M * K * d.D);
+    two(w->y_hi, w->y_lo, cells * d.C); two(w->zf_hi, w->zf_lo, cells * d.C); two(w->h_hi, w->h_lo, cells * d.H);
+    two(w->dG_hi, w->dG_lo, M * K * d.GH); two(w->dAh_hi, w->dAh_lo, cells * d.GH);
+    two(w->dO_hi, w->dO_lo, cells * d.Co); two(w->dzf_hi, w->dzf_lo, cells * d.C);
+    two(w->dC_hi, w->dC_lo, M * K * d.D);
+  }
   w->bytes = round_up_sz(b.off, 256);
 }
 
@@ -239,11 +260,14 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
 
 // cond_transform for all K steps, then the c-part of the gate-ih product (models.py:187-190, 206-208)
 static int cond_to_gates(const Dims &d, const lfi_params *p, const float *WcF, const float *cond, size_t M, float *Cact,
-                         float *G, int mode, void *gws, size_t gws_bytes, cudaStream_t st) {
+                         float *G, int mode, void *gws, size_t gws_bytes, cudaStream_t st, void *cact_hi = nullptr,
+                         void *cact_lo = nullptr) {
   const int K = d.K, D = d.D, GH = d.GH, In = d.Ci + D;
   GemmArgs g = gemm_args(0, 1, (int)M, K * D, d.Fe, cond, d.Fe, WcF, d.Fe, Cact, K * D, LFI_EPI_BIAS | LFI_EPI_LRELU, p->bc);
+  if (cact_hi) g.pOut = plane_ref(cact_hi, cact_lo, K * D);  // the activations leave the epilogue as operand planes too
   LFI_TRY(gemm_dispatch(mode, g, gws, gws_bytes, st));
   GemmArgs h = gemm_args(0, 1, (int)M, GH, D, Cact, K * D, p->w_ih + d.Ci, In, G, K * GH, LFI_EPI_BIAS, p->b_ih);
+  if (cact_hi) h.pA = plane_ref(cact_hi, cact_lo, K * D, D);
   h.batch = K; h.sA = D; h.sB = (long)GH * In; h.sC = GH; h.sBias = GH;
   LFI_TRY(gemm_dispatch(mode, h, gws, gws_bytes, st));
   return LFI_OK;
@@ -323,7 +347,7 @@ int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params 
   const float *WcF = (const float *)derived + L.WcF;
 
   LFI_TRY(build_cond(s, d, p, bt, d.start_ts, Tp, w.cond, w.enc, w.gh, true, false, true, gemm_mode, gws, gws_bytes, st));
-  LFI_TRY(cond_to_gates(d, p, WcF, w.cond, M, w.Cact, w.G, gemm_mode, gws, gws_bytes, st));
+  LFI_TRY(cond_to_gates(d, p, WcF, w.cond, M, w.Cact, w.G, gemm_mode, gws, gws_bytes, st, w.cp ? w.cact_hi : nullptr, w.cp ? w.cact_lo : nullptr));
 
   core::FwdArgs a;
   memset(&a, 0, sizeof(a));
@@ -334,6 +358,7 @@ int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params 
   a.st_ahn = w.st.ahn; a.st_o = w.st.o; a.ld = w.ld; a.ld_accumulate = 0; a.nll = nll; a.z_out = z;
   a.scale_out = scale_out;
   a.flags = w.flags; a.flags_bytes = kFlagInts * sizeof(int);
+  if (w.cp) { a.py_hi = w.y_hi; a.py_lo = w.y_lo; a.pzf_hi = w.zf_hi; a.pzf_lo = w.zf_lo; a.ph_hi = w.h_hi; a.ph_lo = w.h_lo; }
   return core::launch_fwd(a, st);
 }
 
@@ -362,31 +387,46 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   a.dx = w.dx; a.dh = w.dh; a.dc = w.dc; a.dG = w.dG; a.dAh = w.dAh; a.dO = w.dO; a.dzf = w.dzf;
   a.g_an_bias = g->an_bias; a.g_an_logs = g->an_logs; a.g_b_hh = g->b_hh; a.g_bf = g->bf; a.g_lf = g->lf;
   a.flags = w.flags; a.flags_bytes = kFlagInts * sizeof(int);
+  if (w.cp) {
+    a.dG = nullptr; a.dAh = nullptr; a.dO = nullptr; a.dzf = nullptr;
+    a.pdG_hi = w.dG_hi; a.pdG_lo = w.dG_lo; a.pdAh_hi = w.dAh_hi; a.pdAh_lo = w.dAh_lo;
+    a.pdO_hi = w.dO_hi; a.pdO_lo = w.dO_lo; a.pdzf_hi = w.dzf_hi; a.pdzf_lo = w.dzf_lo;
+    a.g_b_ih = g->b_ih;
+  }
   LFI_TRY(core::launch_bwd(a, st));
 
   // 2. weight gradients of the per-step matrices as batched (over k) reductions over the M rows
+  auto off16 = [](void *base, size_t n) -> void * { return base ? (void *)((uint16_t *)base + n) : nullptr; };
   auto wgrad = [&](int Mo, int No, size_t red, const float *A, int lda, long sA, const float *Bm, int ldb, long sB, float *Cm,
-                   int ldc, long sC) -> int {
+                   int ldc, long sC, PlaneRef pa = PlaneRef{nullptr, nullptr, 0, 0}, PlaneRef pb = PlaneRef{nullptr, nullptr, 0, 0}) -> int {
     GemmArgs q = gemm_args(1, 0, Mo, No, (int)red, A, lda, Bm, ldb, Cm, ldc, LFI_EPI_ACCUM);
     q.batch = K; q.sA = sA; q.sB = sB; q.sC = sC;
+    if (w.cp) { q.pA = pa; q.pB = pb; }
     return gemm_dispatch(gemm_mode, q, gws, gws_bytes, st);
   };
+  const PlaneRef pdG = plane_ref(w.dG_hi, w.dG_lo, K * GH, GH), ph = plane_ref(w.h_hi, w.h_lo, H, (long)(M * H));
   if (Tp > 1)  // dW_hh[k] += dA_h[k][t>=1]^T h[k][t-1]
     LFI_TRY(wgrad(GH, H, (size_t)(Tp - 1) * B, w.dAh + (size_t)B * GH, GH, (long)(M * GH), w.st.h, H, (long)(M * H), g->w_hh, H,
-                  (long)GH * H));
-  LFI_TRY(wgrad(GH, Ci, M, w.dG, K * GH, GH, w.st.zf, C, (long)(M * C), g->w_ih, In, (long)GH * In));       // dW_ih[:, :Ci]
-  LFI_TRY(wgrad(GH, D, M, w.dG, K * GH, GH, w.Cact, K * D, D, g->w_ih + Ci, In, (long)GH * In));           // dW_ih[:, Ci:]
-  LFI_TRY(wgrad(Co, H, M, w.dO, Co, (long)(M * Co), w.st.h, H, (long)(M * H), g->wf, H, (long)Co * H));     // dWf
-  LFI_TRY(wgrad(C, C, M, w.st.y, C, (long)(M * C), w.dzf, C, (long)(M * C), g->w, C, (long)C * C));         // dW (1x1 conv)
-  LFI_TRY(aux::colsum(g->b_ih, w.dG, K * GH, (int)M, K * GH, 1.0f, st));
+                  (long)GH * H, plane_ref(off16(w.dAh_hi, (size_t)B * GH), off16(w.dAh_lo, (size_t)B * GH), GH, (long)(M * GH)), ph));
+  LFI_TRY(wgrad(GH, Ci, M, w.dG, K * GH, GH, w.st.zf, C, (long)(M * C), g->w_ih, In, (long)GH * In, pdG,
+                plane_ref(w.zf_hi, w.zf_lo, C, (long)(M * C))));                                                      // dW_ih[:, :Ci]
+  LFI_TRY(wgrad(GH, D, M, w.dG, K * GH, GH, w.Cact, K * D, D, g->w_ih + Ci, In, (long)GH * In, pdG,
+                plane_ref(w.cact_hi, w.cact_lo, K * D, D)));                                                          // dW_ih[:, Ci:]
+  LFI_TRY(wgrad(Co, H, M, w.dO, Co, (long)(M * Co), w.st.h, H, (long)(M * H), g->wf, H, (long)Co * H,
+                plane_ref(w.dO_hi, w.dO_lo, Co, (long)(M * Co)), ph));                                                 // dWf
+  LFI_TRY(wgrad(C, C, M, w.st.y, C, (long)(M * C), w.dzf, C, (long)(M * C), g->w, C, (long)C * C,
+                plane_ref(w.y_hi, w.y_lo, C, (long)(M * C)), plane_ref(w.dzf_hi, w.dzf_lo, C, (long)(M * C))));       // dW (1x1 conv)
+  if (!w.cp) LFI_TRY(aux::colsum(g->b_ih, w.dG, K * GH, (int)M, K * GH, 1.0f, st));  // (planes: reduced inside the core kernel)
 
   // 3. cond_transform backward
   {
     GemmArgs q = gemm_args(0, 0, (int)M, D, GH, w.dG, K * GH, p->w_ih + Ci, In, w.dC, K * D, LFI_EPI_LRELU_BWD);
     q.batch = K; q.sA = GH; q.sB = (long)GH * In; q.sC = D; q.aux = w.Cact; q.ldaux = K * D; q.sAux = D;
+    if (w.cp) { q.pA = pdG; q.pOut = plane_ref(w.dC_hi, w.dC_lo, K * D, D); }
     LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
     LFI_TRY(aux::colsum(g->bc, w.dC, K * D, (int)M, K * D, 1.0f, st));
     GemmArgs r = gemm_args(1, 0, K * D, d.Fe, (int)M, w.dC, K * D, w.cond, d.Fe, w.dWcF, d.Fe, 0);
+    if (w.cp) r.pA = plane_ref(w.dC_hi, w.dC_lo, K * D);
     LFI_TRY(gemm_dispatch(gemm_mode, r, gws, gws_bytes, st));
     LFI_TRY(aux::unfold_wc_grad(g->wc, w.dWcF, d, *s, st));
   }
@@ -397,6 +437,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   if (enc_lo < 0) return LFI_OK;
   {
     GemmArgs q = gemm_args(0, 0, (int)M, d.Fe - enc_lo, K * D, w.dC, K * D, WcF + enc_lo, d.Fe, w.dcond + enc_lo, d.Fe, 0);
+    if (w.cp) q.pA = plane_ref(w.dC_hi, w.dC_lo, K * D);
     LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
   }
 
@@ -412,7 +453,6 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
     LFI_TRY(aux::gather_windows(w.xg, dim, 1, bt->x[m], bt->mask[m], B, T, dim, hist, 1, d.start_ts, Tp, st));
     if (ew.planes) LFI_TRY(split_to_planes(w.xg, (int)(hist * M), dim, dim, 0, 1, ew.xg_hi, lo ? ew.xg_lo : nullptr, st));
     LFI_TRY(aux::fill(w.dhe, 0.f, M * E, st));
-    auto off16 = [](void *base, size_t n) -> void * { return base ? (void *)((uint16_t *)base + n) : nullptr; };
     const bool fused = ew.planes && (E == 64 || E == 128 || E == 192 || E == 256) && env_flag("LFI_FUSED_GRU_BWD", false);
     for (int sidx = hist - 1; sidx >= 0; --sidx) {
       aux::EncStepBwd2 e;
