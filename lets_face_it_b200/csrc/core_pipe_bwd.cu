@@ -98,6 +98,7 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
   const int *wait_flag = progress + ((size_t)(p * K + k + 1) * 2 + c);
   int *my_flag = progress + ((size_t)(p * K + k) * 2 + c);
   int it = 0;
+  bool x3_pending = false;
 
   // per-channel gradient accumulators (flushed once at the end)
   float gbhh[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, gbin[2] = {0.f, 0.f};
@@ -178,6 +179,7 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
         if (q < Ci) dzf[r * pC + q] = dx1;
       }
       __syncthreads();
+      if (x3_pending) { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); x3_pending = false; }  // peer done with buffer 1
       for (int e = tid; e < Co * PRH; e += PNT) {  // dlin in act layout, to both CTAs
         const int j = e / PRH, r = e - j * PRH;
         const float v = dor[r * pO + j];
@@ -191,6 +193,15 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
         if (a.pdO_hi) put_plane(a.pdO_hi, a.pdO_lo, o, dor[r * pO + j]);
       }
       cluster.sync();  // X1: dlin of all 64 rows present in both CTAs
+      if (t < Tp - 1) {
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {  // the peer's share of d h[k][t] (it rewrites this buffer only after X2 of this frame)
+          const float4 v0 = *reinterpret_cast<const float4 *>(dhc + (u0 + x) * PHS + 8 * rg);
+          const float4 v1 = *reinterpret_cast<const float4 *>(dhc + (u0 + x) * PHS + 8 * rg + 4);
+          carry[0][x] += v0.x; carry[1][x] += v0.y; carry[2][x] += v0.z; carry[3][x] += v0.w;
+          carry[4][x] += v1.x; carry[5][x] += v1.y; carry[6][x] += v1.z; carry[7][x] += v1.w;
+        }
+      }
 
       // ---- 3. dh = dlin @ Wf (+ carried gradient) for this thread's rows x units ---------------------------------------
       float dh[8][2];
@@ -295,26 +306,16 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
           jp[1][0] = fmaf(av.y, wv.x, jp[1][0]); jp[1][1] = fmaf(av.y, wv.y, jp[1][1]); jp[1][2] = fmaf(av.y, wv.z, jp[1][2]); jp[1][3] = fmaf(av.y, wv.w, jp[1][3]);
         }
       };
+      // 5a. dz1 partial sums: on the stage-to-stage path
       stage_to(buf0, dar);
       __syncthreads();               // every thread is past step 3: buffer 1 (= dlin) is free
       stage_to(buf1, dau);
-      acc_i(buf0, 0); acc_j(buf0, 0);
+      acc_j(buf0, 0);
       __syncthreads();
       stage_to(buf0, dan);
-      acc_i(buf1, 1); acc_j(buf1, 1);
+      acc_j(buf1, 1);
       __syncthreads();
-      stage_to(buf1, dnr);
       acc_j(buf0, 2);
-      __syncthreads();
-      acc_i(buf1, 2);
-#pragma unroll
-      for (int x = 0; x < 2; ++x) {
-        float *pq = peer + pl.dhc + (u0 + x) * PHS + 8 * rg;
-        *reinterpret_cast<float4 *>(pq) = make_float4(ip[0][2 + x], ip[1][2 + x], ip[2][2 + x], ip[3][2 + x]);
-        *reinterpret_cast<float4 *>(pq + 4) = make_float4(ip[4][2 + x], ip[5][2 + x], ip[6][2 + x], ip[7][2 + x]);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) carry[r][x] += ip[r][x];
-      }
       if (jact) {
         const int dest = (2 * jrp) / PRH, lr = (2 * jrp) % PRH;
         float *ob = (dest == c ? sm : peer) + pl.dz1 + c * PRH * PZ1 + lr * PZ1 + 4 * jcq;
@@ -324,13 +325,6 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
       cluster.sync();  // X2: partial sums exchanged
 
       // ---- 6. finish d(1x1 conv output), dy = dzf @ W^T, ActNorm backward (modules.py:45-66) ------------------------------
-#pragma unroll
-      for (int x = 0; x < 2; ++x) {  // the peer's share of d h[k][t-1] (read before the next X1: the peer rewrites it after that)
-        const float4 v0 = *reinterpret_cast<const float4 *>(dhc + (u0 + x) * PHS + 8 * rg);
-        const float4 v1 = *reinterpret_cast<const float4 *>(dhc + (u0 + x) * PHS + 8 * rg + 4);
-        carry[0][x] += v0.x; carry[1][x] += v0.y; carry[2][x] += v0.z; carry[3][x] += v0.w;
-        carry[4][x] += v1.x; carry[5][x] += v1.y; carry[6][x] += v1.z; carry[7][x] += v1.w;
-      }
       for (int e = tid; e < PRH * Ci; e += PNT) {
         const int r = e / Ci, i = e - r * Ci;
         dzf[r * pC + i] += dz1[r * PZ1 + i] + dz1[PRH * PZ1 + r * PZ1 + i];
@@ -375,8 +369,28 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
         __syncthreads();
         if (tid == 0) { __threadfence(); st_release_gpu_b(my_flag, it + 1); }
       }
+      // 5b. dh_prev partial sums: needed by this stage's next frame only, so they run after the hand-off to stage k-1.
+      //     Buffer 1 still holds dau; buffer 0 (dan) is free since X2.
+      stage_to(buf0, dar);
+      acc_i(buf1, 1);
+      __syncthreads();
+      stage_to(buf1, dnr);
+      acc_i(buf0, 0);
+      __syncthreads();
+      acc_i(buf1, 2);
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        float *pq = peer + pl.dhc + (u0 + x) * PHS + 8 * rg;
+        *reinterpret_cast<float4 *>(pq) = make_float4(ip[0][2 + x], ip[1][2 + x], ip[2][2 + x], ip[3][2 + x]);
+        *reinterpret_cast<float4 *>(pq + 4) = make_float4(ip[4][2 + x], ip[5][2 + x], ip[6][2 + x], ip[7][2 + x]);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) carry[r][x] += ip[r][x];
+      }
+      // X3 (split): this CTA is done with both staging buffers and has delivered the peer's dh_prev share
+      asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+      x3_pending = true;
     }
-    cluster.sync();
+    if (x3_pending) { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); x3_pending = false; }
   }
 
   // ---- flush the per-channel gradients -------------------------------------------------------------------------------
