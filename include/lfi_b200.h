@@ -175,6 +175,7 @@ int lfi_clip_adam(float *theta, float *grad, float *m, float *v, size_t n, float
 #define LFI_EPI_LRELU 2
 #define LFI_EPI_ACCUM 4
 #define LFI_EPI_LRELU_BWD 8
+#define LFI_EPI_ACCUM_PRE 16 /* add the old C before bias/activation: C = act(C + A B + bias) */
 int lfi_gemm(int mode, int transA, int transB, int M, int N, int K, const float *A, int lda, long strideA,
              const float *B, int ldb, long strideB, float *C, int ldc, long strideC, const float *bias,
              long strideBias, const float *aux, int ldaux, long strideAux, int batch, int epi, void *ws,

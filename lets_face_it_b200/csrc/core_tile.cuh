@@ -17,7 +17,8 @@ constexpr int RG = NT / TX;    // row groups
 constexpr int CPT = 6;         // columns per thread per chunk
 constexpr int WCH = TX * CPT;  // 384 columns per chunk
 constexpr int KC = 16;         // reduction rows per weight stage
-constexpr int WST_FLOATS = 2 * KC * WCH;
+constexpr int NSTG = 4;        // weight stages in flight (ring): covers the L2 latency of the stream
+constexpr int WST_FLOATS = NSTG * KC * WCH;
 
 __device__ __forceinline__ void cp_async16(float *smem, const float *g) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -78,14 +79,17 @@ __device__ __forceinline__ void tile_gemm(const float *act, const float *__restr
         cp_async16(dst + i * WCH + c4 * 4, Wg + (size_t)(k0 + i) * ldw + n0 + c4 * 4);
       }
     };
-    load_stage(0, 0);
-    cp_async_commit();
-    for (int s = 0; s < nst; ++s) {
-      if (s + 1 < nst) load_stage((s + 1) & 1, s + 1);
+#pragma unroll
+    for (int s = 0; s < NSTG - 1; ++s) {
+      if (s < nst) load_stage(s, s);
       cp_async_commit();
-      cp_async_wait<1>();
-      __syncthreads();
-      const float *w = wst + (s & 1) * (KC * WCH);
+    }
+    for (int s = 0; s < nst; ++s) {
+      cp_async_wait<NSTG - 2>();   // stage s has landed
+      __syncthreads();             // ... for every thread; and everyone is done with the buffer of stage s-1
+      if (s + NSTG - 1 < nst) load_stage((s + NSTG - 1) % NSTG, s + NSTG - 1);
+      cp_async_commit();
+      const float *w = wst + (s % NSTG) * (KC * WCH);
       const int k0 = s * KC;
       const int kk = min(KC, Kin - k0);
 #pragma unroll 4
@@ -102,8 +106,8 @@ __device__ __forceinline__ void tile_gemm(const float *act, const float *__restr
 #pragma unroll
           for (int c = 0; c < CPT; ++c) acc[r][c] = fmaf(a[r], wv[c], acc[r][c]);
       }
-      __syncthreads();
     }
+    __syncthreads();  // the ring may be refilled (next column chunk / next product)
     cp_async_wait<0>();
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {

@@ -126,10 +126,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g, int splitk) 
       const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (n >= g.N) continue;
       float v = acc[i][j];
+      float *c = C + (size_t)m * g.ldc + n;
+      if (g.epi & LFI_EPI_ACCUM_PRE) v += *c;
       if (g.epi & LFI_EPI_BIAS) v += bias[n];
       if (g.epi & LFI_EPI_LRELU) v = v > 0.f ? v : kLeaky * v;
       if (g.epi & LFI_EPI_LRELU_BWD) v *= (aux[(size_t)m * g.ldaux + n] > 0.f ? 1.f : kLeaky);
-      float *c = C + (size_t)m * g.ldc + n;
       if (splitk > 1) atomicAdd(c, v);
       else if (g.epi & LFI_EPI_ACCUM) *c += v;
       else *c = v;

@@ -469,6 +469,7 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
     const int rr = lane & 7, cg = (lane >> 3) * 4;
     const bool want_c = p.C != nullptr;
     const bool rmw = (p.epi & LFI_EPI_ACCUM) && p.splitk == 1;
+    const bool rmw_pre = (p.epi & LFI_EPI_ACCUM_PRE) != 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const TileCoord t = tile_coord(p, tile, nkb);
@@ -495,9 +496,9 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
           const int n = nc0 + cg;  // N % 4 == 0 in vec mode: a 4-group is entirely inside or outside
           const bool ncol_ok = n < p.N;
           float4 pre[4];
-          if (ncol_ok && (rmw || aux)) {
-            const float *src = rmw ? C : aux;
-            const int ld = rmw ? p.ldc : p.ldaux;
+          if (ncol_ok && (rmw || rmw_pre || aux)) {
+            const float *src = (rmw || rmw_pre) ? C : aux;
+            const int ld = (rmw || rmw_pre) ? p.ldc : p.ldaux;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int m = mrow0 + rr + 8 * i;
@@ -527,6 +528,7 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float y = has_work ? x[e] : 0.f;
+                if (rmw_pre) y += a4[e];
                 y += b4[e];
                 if (p.epi & LFI_EPI_LRELU) y = y > 0.f ? y : kLeaky * y;
                 if (aux) y *= (a4[e] > 0.f ? 1.f : kLeaky);
@@ -569,6 +571,7 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
               const int n = nc0 + j;
               if (n >= p.N) break;
               float y = has_work ? __uint_as_float(v[j]) : 0.f;
+              if (rmw_pre) y += C[(size_t)m * p.ldc + n];
               if (bias) y += bias[n];
               if (p.epi & LFI_EPI_LRELU) y = y > 0.f ? y : kLeaky * y;
               if (aux) y *= (aux[(size_t)m * p.ldaux + n] > 0.f ? 1.f : kLeaky);

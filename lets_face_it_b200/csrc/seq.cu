@@ -508,8 +508,17 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
 struct SampleWs {
   float *cond, *Cs, *G, *gh, *hstate, *cstate;
   EncWs enc[LFI_NMOD];
+  // tensor-core modes, autoregressive sampling: per-frame conditioning GEMMs (see lfi_seq_sample)
+  bool tc_ar;
+  float *car;                       // [B][Far]   p1_face window of the current frame
+  void *war_hi, *war_lo;            // [K*D][Far] autoregressive columns of the folded cond_transform weight
+  void *wihc_hi, *wihc_lo;          // [K][GH][D] W_ih[:, Ci:]
+  void *cact_hi, *cact_lo;          // [B][K*D]   cond_transform activations of the current frame
   size_t bytes;
 };
+static bool sample_tc_ar(const Dims &d, int mode) {
+  return mode != LFI_GEMM_FP32 && d.Far > 0 && d.Far % 8 == 0 && d.D % 8 == 0 && env_flag("LFI_SAMPLE_TC", true);
+}
 static void plan_sample(const lfi_shape *s, const Dims &d, int B, int T, int chunk, int mode, void *ws, SampleWs *w) {
   Bump b(ws, 0);
   const size_t Mc = (size_t)chunk * B, K = d.K;
@@ -535,6 +544,14 @@ static void plan_sample(const lfi_shape *s, const Dims &d, int B, int T, int chu
     if (Mc * 3 * E > ghmax) ghmax = Mc * 3 * E;
   }
   w->gh = b.take<float>(ghmax);
+  w->tc_ar = sample_tc_ar(d, mode);
+  if (w->tc_ar) {
+    const bool lo = mode == LFI_GEMM_BF16X3;
+    w->car = b.take<float>((size_t)B * d.Far);
+    w->war_hi = take_bf16(b, K * d.D * d.Far);            w->war_lo = lo ? take_bf16(b, K * d.D * d.Far) : nullptr;
+    w->wihc_hi = take_bf16(b, K * d.GH * d.D);            w->wihc_lo = lo ? take_bf16(b, K * d.GH * d.D) : nullptr;
+    w->cact_hi = take_bf16(b, (size_t)B * K * d.D);       w->cact_lo = lo ? take_bf16(b, (size_t)B * K * d.D) : nullptr;
+  }
   w->bytes = round_up_sz(b.off, 256);
 }
 
@@ -617,6 +634,36 @@ int lfi_seq_sample(const lfi_shape *s, const void *derived, const lfi_params *p,
     }
     a.faces_out = faces; a.fo_sb = (long)seq_len * d.C; a.fo_st = d.C;
     a.hstate = w.hstate; a.cstate = w.cstate; a.logdet_out = logdet_out;
+    if (!teacher_forced && w.tc_ar) {
+      // Tensor-core modes: the autoregressive part of the conditioning (p1_face window -> cond_transform -> gate-ih,
+      // 340 k of the 410 k MAC per row and step) runs as two tcgen05 GEMMs per frame over all sequences; the persistent
+      // kernel then walks the K inverse steps of that frame with the gate pre-activations given.  Still no host round
+      // trip: everything is stream-ordered.
+      const bool lo = gemm_mode == LFI_GEMM_BF16X3;
+      const int In = d.Ci + d.D, hist0 = d.Far / d.C;
+      if (c0 == 0) {  // operand planes of the two weights, once per call
+        LFI_TRY(split_to_planes(WcF, K * d.D, d.Far, d.Fe, 0, 1, w.war_hi, lo ? w.war_lo : nullptr, st));
+        LFI_TRY(split_to_planes(p->w_ih + d.Ci, d.GH, d.D, In, (long)d.GH * In, K, w.wihc_hi, lo ? w.wihc_lo : nullptr, st));
+      }
+      a.cstatic = nullptr; a.faces = nullptr;
+      a.Tc = 1; a.G = w.G; a.g_ld = (long)K * d.GH;
+      for (int tc = 0; tc < Tc; ++tc) {
+        LFI_TRY(aux::gather_windows(w.car, d.Far, 0, faces, nullptr, B, seq_len, d.C, hist0, 0, t0 + tc, 1, st));
+        float *Cf = w.Cs + (size_t)tc * B * K * d.D;  // static pre-activation of this frame (bias included), updated in place
+        GemmArgs q = gemm_args(0, 1, B, K * d.D, d.Far, w.car, d.Far, nullptr, d.Far, Cf, K * d.D, LFI_EPI_ACCUM_PRE | LFI_EPI_LRELU);
+        q.pB = plane_ref(w.war_hi, w.war_lo, d.Far);
+        q.pOut = plane_ref(w.cact_hi, w.cact_lo, K * d.D);
+        LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
+        GemmArgs h = gemm_args(0, 1, B, d.GH, d.D, nullptr, K * d.D, nullptr, d.D, w.G, K * d.GH, LFI_EPI_BIAS, p->b_ih);
+        h.batch = K; h.sC = d.GH; h.sBias = d.GH;
+        h.pA = plane_ref(w.cact_hi, w.cact_lo, K * d.D, d.D);
+        h.pB = plane_ref(w.wihc_hi, w.wihc_lo, d.D, (long)d.GH * d.D);
+        LFI_TRY(gemm_dispatch(gemm_mode, h, gws, gws_bytes, st));
+        a.t_abs0 = t0 + tc; a.t_rel0 = c0 + tc;
+        LFI_TRY(core::launch_inv(a, st));
+      }
+      continue;
+    }
     LFI_TRY(core::launch_inv(a, st));
   }
   return LFI_OK;
