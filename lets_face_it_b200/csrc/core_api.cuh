@@ -86,6 +86,8 @@ int choose_rpt(const Dims &d, int B, bool bwd, bool sampler);
 int launch_fwd(const FwdArgs &a, cudaStream_t st);
 int launch_inv(const InvArgs &a, cudaStream_t st);
 int launch_bwd(const BwdArgs &a, cudaStream_t st);
+bool inv_rows_supported(const InvArgs &a);
+int launch_inv_rows(const InvArgs &a, cudaStream_t st);
 
 }  // namespace core
 }  // namespace lfi

@@ -356,6 +356,7 @@ template <int RPT> static int launch_inv_t(const InvArgs &a, cudaStream_t st) {
 }
 
 int launch_inv(const InvArgs &a, cudaStream_t st) {
+  if (inv_rows_supported(a)) return launch_inv_rows(a, st);
   const int rpt = choose_rpt(a.d, a.B, false, true);
   switch (rpt) {
     case 8: return launch_inv_t<8>(a, st);
