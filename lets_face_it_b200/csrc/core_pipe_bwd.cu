@@ -132,6 +132,28 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
           }
         }
       }
+      // coupling stash of this CTA's rows (lane = coupling channel, row = warp + 8n): independent of stage k+1, requested
+      // before the wait so that the latency hides behind it
+      constexpr int NR = PRH / 8;
+      float c_dnl[NR], c_z2[NR];
+      float2 c_o[NR];
+#pragma unroll
+      for (int n = 0; n < NR; ++n) {
+        const int r = warp + 8 * n, q = lane;
+        c_dnl[n] = 0.f; c_z2[n] = 0.f; c_o[n] = make_float2(0.f, 0.f);
+        if (r < nmy) {
+          const int b = row0 + lr0 + r;
+          c_dnl[n] = a.dnll[(size_t)t * B + b];
+          if (q < Cz) {
+            if (d.affine) {
+              c_o[n] = *reinterpret_cast<const float2 *>(a.st.o + (cell * B + b) * Co + 2 * q);
+              c_z2[n] = a.st.zf[(cell * B + b) * C + Ci + q];
+            } else {
+              c_o[n].x = a.st.o[(cell * B + b) * Co + q];
+            }
+          }
+        }
+      }
       // ---- 1. wait for stage k+1 ---------------------------------------------------------------------------------------
       if (!lastk) {
         if (tid == 0) {
@@ -139,44 +161,48 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
         }
         __syncthreads();
       }
-      // ---- 2. coupling backward (models.py:331-341) on this CTA's 32 rows: lane = coupling channel ------------------
+      // ---- 2. coupling backward (models.py:331-341) on this CTA's 32 rows ---------------------------------------------
+      float c_dz[NR], c_dx1[NR];
 #pragma unroll
-      for (int n = 0; n < PRH / 8; ++n) {
+      for (int n = 0; n < NR; ++n) {  // the published d(output of step k): all requests first
         const int r = warp + 8 * n, q = lane;
-        float dz2 = 0.f, dl0 = 0.f, dl1 = 0.f, dx1 = 0.f;
+        c_dz[n] = 0.f; c_dx1[n] = 0.f;
         if (r < nmy) {
           const int b = row0 + lr0 + r;
-          const float dnl = a.dnll[(size_t)t * B + b];
-          const float dld = -dnl / kLn2;  // d nll / d logdet
           const float *dxp = a.dx + ((cell + Tp) * B + b) * C;
           const float *zp = a.z + ((size_t)t * B + b) * C;
-          if (q < Cz) {
-            const float dz2n = lastk ? dnl * zp[Ci + q] / kLn2 : __ldcg(dxp + Ci + q);  // last step: d nll / d z = z / ln2
-            if (d.affine) {
-              const float2 o2 = *reinterpret_cast<const float2 *>(a.st.o + (cell * B + b) * Co + 2 * q);
-              const float shift = o2.x, sc = o2.y;
-              const float z2 = a.st.zf[(cell * B + b) * C + Ci + q];
-              const float sg = sigmoidf_(sc + 2.0f), s = fmaxf(sg, d.eps);
-              const float ds = dz2n * (z2 + shift) + dld / s;
-              dz2 = dz2n * s;
-              const float dsc = (sg >= d.eps) ? ds * sg * (1.0f - sg) : 0.f;
-              gbf[0] += dz2; gbf[1] += dsc; glf[0] += dz2 * shift; glf[1] += dsc * sc;
-              dl0 = dz2 * e3[2 * q]; dl1 = dsc * e3[2 * q + 1];
-            } else {
-              const float ov = a.st.o[(cell * B + b) * Co + q];
-              dz2 = dz2n;
-              gbf[0] += dz2n; glf[0] += dz2n * ov;
-              dl0 = dz2n * e3[q];
-            }
+          if (q < Cz) c_dz[n] = lastk ? c_dnl[n] * zp[Ci + q] / kLn2 : __ldcg(dxp + Ci + q);  // last step: d nll / d z = z / ln2
+          if (q < Ci) c_dx1[n] = lastk ? c_dnl[n] * zp[q] / kLn2 : __ldcg(dxp + q);
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < NR; ++n) {
+        const int r = warp + 8 * n, q = lane;
+        float dz2 = 0.f, dl0 = 0.f, dl1 = 0.f;
+        if (r < nmy && q < Cz) {
+          const float dld = -c_dnl[n] / kLn2;  // d nll / d logdet
+          const float dz2n = c_dz[n];
+          if (d.affine) {
+            const float shift = c_o[n].x, sc = c_o[n].y, z2 = c_z2[n];
+            const float sg = sigmoidf_(sc + 2.0f), s = fmaxf(sg, d.eps);
+            const float ds = dz2n * (z2 + shift) + dld / s;
+            dz2 = dz2n * s;
+            const float dsc = (sg >= d.eps) ? ds * sg * (1.0f - sg) : 0.f;
+            gbf[0] += dz2; gbf[1] += dsc; glf[0] += dz2 * shift; glf[1] += dsc * sc;
+            dl0 = dz2 * e3[2 * q]; dl1 = dsc * e3[2 * q + 1];
+          } else {
+            const float ov = c_o[n].x;
+            dz2 = dz2n;
+            gbf[0] += dz2n; glf[0] += dz2n * ov;
+            dl0 = dz2n * e3[q];
           }
-          if (q < Ci) dx1 = lastk ? dnl * zp[q] / kLn2 : __ldcg(dxp + q);
         }
         if (q < Cz) {
           dzf[r * pC + Ci + q] = dz2;
           if (d.affine) { dor[r * pO + 2 * q] = dl0; dor[r * pO + 2 * q + 1] = dl1; }
           else dor[r * pO + q] = dl0;
         }
-        if (q < Ci) dzf[r * pC + q] = dx1;
+        if (q < Ci) dzf[r * pC + q] = c_dx1[n];
       }
       __syncthreads();
       if (x3_pending) { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); x3_pending = false; }  // peer done with buffer 1

@@ -75,7 +75,25 @@ core_fwd_pipe(const FwdArgs a, const int P, const int ntiles, int *progress) {
 
     for (int t = 0; t < Tp; ++t, ++it) {
       const size_t cell = (size_t)k * Tp + t;
-      // ---- 0. prefetch the gate-ih pre-activations; recurrent product h . W_hh^T (no dependence on stage k-1)
+      // ---- 0. If stage k-1 has already published this frame (the common case: it runs ahead), request the input now so
+      //         that its latency hides behind the recurrent product; otherwise it is fetched after the wait below.
+      constexpr int XI = (PRH * 64 + PNT - 1) / PNT;  // C <= 64
+      float xv[XI];
+      bool have_x = first || ld_acquire_gpu(wait_flag) > it;
+      have_x = __syncthreads_and(have_x);   // uniform decision (also orders the previous frame's shared-memory traffic)
+      auto fetch_x = [&]() {
+#pragma unroll
+        for (int i = 0; i < XI; ++i) {
+          const int e = tid + PNT * i, r = e / C, cc = e - r * C;
+          xv[i] = 0.f;
+          if (e < PRH * C && r < nmy) {
+            const int b = row0 + lr0 + r;
+            xv[i] = first ? a.x0[(size_t)b * a.x_sb + (size_t)t * a.x_st + cc] : __ldcg(a.xin + (cell * B + b) * C + cc);
+          }
+        }
+      };
+      if (have_x) fetch_x();
+      //         prefetch the gate-ih pre-activations; recurrent product h . W_hh^T (no dependence on stage k-1)
       float2 gp[8][3];
       {
         const float *Gb = a.G + ((size_t)t * B + row0 + 8 * rg) * a.g_ld + (size_t)(k - a.g_k0) * GH + PUC * c + u0;
@@ -116,23 +134,26 @@ core_fwd_pipe(const FwdArgs a, const int P, const int ntiles, int *progress) {
       }
 
       // ---- 1. wait for stage k-1, ActNorm (modules.py:45-66) on this CTA's 32 rows ---------------------------------
-      if (!first) {
+      if (!have_x) {
         if (tid == 0) {
           while (ld_acquire_gpu(wait_flag) <= it) { }
         }
         __syncthreads();
+        fetch_x();
       }
-      for (int e = tid; e < PRH * C; e += PNT) {
-        const int r = e / C, cc = e - r * C;
-        float v = 0.f;
-        if (r < nmy) {
-          const int b = row0 + lr0 + r;
-          const float x = first ? a.x0[(size_t)b * a.x_sb + (size_t)t * a.x_st + cc] : __ldcg(a.xin + (cell * B + b) * C + cc);
-          v = (x + anb[cc]) * ans[cc];
-          if (a.st_y) a.st_y[(cell * B + b) * C + cc] = v;
-          if (a.py_hi) put_plane(a.py_hi, a.py_lo, (cell * B + b) * C + cc, v);
+#pragma unroll
+      for (int i = 0; i < XI; ++i) {
+        const int e = tid + PNT * i, r = e / C, cc = e - r * C;
+        if (e < PRH * C) {
+          float v = 0.f;
+          if (r < nmy) {
+            const int b = row0 + lr0 + r;
+            v = (xv[i] + anb[cc]) * ans[cc];
+            if (a.st_y) a.st_y[(cell * B + b) * C + cc] = v;
+            if (a.py_hi) put_plane(a.py_hi, a.py_lo, (cell * B + b) * C + cc, v);
+          }
+          xs[r * pC + cc] = v;
         }
-        xs[r * pC + cc] = v;
       }
       __syncthreads();
       // ---- 2. invertible 1x1 conv (modules.py:186): z = y @ W, 2 rows x 4 columns per thread -------------------------
@@ -270,7 +291,10 @@ core_fwd_pipe(const FwdArgs a, const int P, const int ntiles, int *progress) {
       // ---- 5. affine coupling (models.py:331-341), log-det, NLL on the last step (modules.py:207-212, models.py:563-565)
       {
         const float *o0 = osm, *o1 = osm + PRH * pO;
-        for (int r = warp; r < nmy; r += PNT / 32) {
+        float ldv = 0.f;  // running log-det of row warp + 8 * lane: one round trip for the warp's rows
+        if ((!first || a.ld_accumulate) && warp + (PNT / 32) * lane < nmy)
+          ldv = __ldcg(a.ld + (size_t)t * B + row0 + lr0 + warp + (PNT / 32) * lane);
+        for (int r = warp, n = 0; r < nmy; r += PNT / 32, ++n) {
           const int b = row0 + lr0 + r;
           float lsum = 0.f;
           for (int q = lane; q < Cz; q += 32) {
@@ -291,8 +315,7 @@ core_fwd_pipe(const FwdArgs a, const int P, const int ntiles, int *progress) {
           }
           lsum = warp_sum(lsum);
           __syncwarp();
-          float ld = lsum;
-          if (!first || a.ld_accumulate) ld += __ldcg(a.ld + (size_t)t * B + b);
+          const float ld = lsum + __shfl_sync(0xffffffffu, ldv, n);
           if (last && a.nll) {
             float zsq = 0.f;
             for (int cc = lane; cc < C; cc += 32) { const float z = zrow[r * pC + cc]; zsq += z * z; }
