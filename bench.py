@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=32, help="sequences per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--no-sample", action="store_true")
     ap.add_argument("--no-bf16", action="store_true", help="skip the secondary bf16-mode timing")
+    ap.add_argument("--variant", default="final", choices=["final", "wide-lstm", "wide-gru"],
+                    help="final = final_model.yaml (the headline); wide-* = BASELINE.json configs[4]: 2x flow depth (K=32), "
+                         "2x hidden size (H=256), LSTM or GRU coupling cell")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling helper: warm up, then run ONE step between cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no bench line")
@@ -61,7 +64,7 @@ def peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -72,11 +75,14 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) host epoch seconds of the timed region: only samples inside it are used (the sampler is started
+        before the warm-up so that nvidia-smi is already running when the region begins)."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
@@ -92,6 +98,10 @@ class ClockSampler:
                 if len(f) < 9:
                     continue
                 try:
+                    if window is not None:
+                        ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                        if ts < window[0] - 0.05 or ts > window[1] + 0.05:
+                            continue
                     sm.append(float(f[1])); mx.append(float(f[2]))
                 except ValueError:
                     continue
@@ -197,6 +207,10 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     hp = load_hparams()
+    if a.variant != "final":
+        hp.Glow["K"] = 32
+        hp.Glow["hidden_channels"] = 256
+        hp.Glow["rnn_type"] = "lstm" if a.variant == "wide-lstm" else "gru"
     hy = O.Hyper.from_hparams(hp)
     gemm_mode = {"fp32": cabi.GEMM_FP32, "bf16x3": cabi.GEMM_BF16X3, "bf16": cabi.GEMM_BF16}[a.gemm]
     B, T = a.batch, T_TRAIN
@@ -236,6 +250,9 @@ def run_ours(a):
         return float(ms)
 
     # ---- device-resident throughput --------------------------------------------------------------------------
+    clocks = ClockSampler(local)
+    if not a.ncu_step:
+        clocks.start()
     for _ in range(max(a.warmup, 3)):
         trainer.step(dbatch)
     if a.ncu_step:
@@ -245,12 +262,12 @@ def run_ours(a):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    clocks = ClockSampler(local)
-    clocks.start()
     n0 = L.lfi_launch_count()
+    t_w0 = time.time()
     ms = timed(lambda: trainer.step(dbatch), a.steps)
+    t_w1 = time.time()
     launches = L.lfi_launch_count() - n0
-    clk = clocks.stop()
+    clk = clocks.stop((t_w0, t_w1))
     frames_step = B * Tp * world
     value = frames_step * a.steps / (ms / 1e3)
 
@@ -288,8 +305,10 @@ def run_ours(a):
         "metric": "train frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if a.gemm != "bf16" else "bf16", "data": "synthetic",
-        "config": {"workload": "final_model.yaml training step (fwd+NLL+bwd+clip20+Adam), B=%d sequences/GPU, T=80 (56 trained "
-                               "frames/seq), frame dropout on" % B, "global_batch": B * world, "gemm_mode": a.gemm,
+        "config": {"workload": "%s training step (fwd+NLL+bwd+clip20+Adam), B=%d sequences/GPU, T=80 (56 trained "
+                               "frames/seq), frame dropout on" % ("final_model.yaml" if a.variant == "final" else
+                                                                  "wide variant (K=32, H=256, %s)" % hp.Glow["rnn_type"], B),
+                   "global_batch": B * world, "gemm_mode": a.gemm,
                    "l2": "per-step working set (activation stash + GEMM operands, >5 GB) far exceeds the 126 MB L2; no flush needed",
                    "parallelism": "dp%d" % world},
         "clocks": clk,
