@@ -103,6 +103,27 @@ __device__ __forceinline__ void tma_load_3d(void *smem, const CUtensorMap *map, 
       : "memory");
 }
 
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, each of which also gets the
+// complete_tx on its own barrier at the same offset
+__device__ __forceinline__ void tma_load_3d_mc(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_wait() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -156,11 +177,13 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
 
 struct TileCoord { int b, m0, n0, kb0, kb1; };
 
-__device__ __forceinline__ TileCoord tile_coord(const Params &p, int tile, int nkb) {
+// CL = 2: the two CTAs of a cluster take the row tiles 2i and 2i+1 of the same column tile and share its B operand
+__device__ __forceinline__ TileCoord tile_coord(const Params &p, int tile, int nkb, int CL = 1, int rank = 0) {
   // n fastest, then m, then split-k, then batch: CTAs running side by side share the A rows through L2
   TileCoord t;
   const int tn = tile % p.tiles_n; tile /= p.tiles_n;
-  const int tm = tile % p.tiles_m; tile /= p.tiles_m;
+  const int tmm = p.tiles_m / CL;
+  const int tm = (tile % tmm) * CL + rank; tile /= tmm;
   const int sk = tile % p.splitk;  tile /= p.splitk;
   t.b = tile; t.m0 = tm * BM; t.n0 = tn * p.bn;
   const int per = (nkb + p.splitk - 1) / p.splitk;
@@ -353,7 +376,7 @@ __device__ __forceinline__ void gru_bwd_tile(const Params &p, const TileCoord &t
   if (!waited) { mbar_wait(tfull, aph); tc_fence_after(); }
 }
 
-template <int FUSE>
+template <int FUSE, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1) {
@@ -370,10 +393,12 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.K + BK - 1) / BK;
-  const int ntiles = p.tiles_m * p.tiles_n * p.splitk * p.batch;
+  const int ntiles = (p.tiles_m / CL) * p.tiles_n * p.splitk * p.batch;  // per cluster
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int tile0 = blockIdx.x / CL, tstride = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 1) {
@@ -383,14 +408,15 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CL > 1) cluster_arrive_wait();  // the peer's barriers are initialised before anything is multicast into them
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const TileCoord t = tile_coord(p, tile, nkb);
+      for (int tile = tile0; tile < ntiles; tile += tstride) {
+        const TileCoord t = tile_coord(p, tile, nkb, CL, rank);
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], stage_bytes);
@@ -409,6 +435,16 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
               // 64 hidden units x (r, u, n): three 64-row boxes of W_hh, 8-row swizzle atoms stay contiguous
               const int u0 = (t.n0 / 192) * 64;
               for (int g = 0; g < 3; ++g) tma_load_3d(sb + pl * b_plane + g * (64 * 128), mb, &full[s], k0, g * p.gru.E + u0, t.b);
+            } else if (CL > 1) {
+              // this CTA fetches its half of the shared B tile and multicasts it to both CTAs of the cluster
+              if (!p.b_mn) {
+                const int half_rows = p.bn / 2;
+                tma_load_3d_mc(sb + pl * b_plane + rank * half_rows * 128, mb, &full[s], k0, t.n0 + rank * half_rows, t.b, (uint16_t)3);
+              } else {
+                const int hc = p.bn / 128;  // 64-wide chunks per CTA
+                for (int j = rank * hc; j < (rank + 1) * hc; ++j)
+                  tma_load_3d_mc(sb + pl * b_plane + j * (BK * 128), mb, &full[s], t.n0 + 64 * j, k0, t.b, (uint16_t)3);
+              }
             } else if (!p.b_mn) {
               tma_load_3d(sb + pl * b_plane, mb, &full[s], k0, t.n0, t.b);
             } else {
@@ -428,8 +464,8 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
       const uint32_t a_adv = p.a_mn ? (UK * 128) >> 4 : (UK * 2) >> 4;  // descriptor address step per UMMA_K
       const uint32_t b_adv = p.b_mn ? (UK * 128) >> 4 : (UK * 2) >> 4;
       int s = 0; uint32_t ph = 0; int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const TileCoord t = tile_coord(p, tile, nkb);
+      for (int tile = tile0; tile < ntiles; tile += tstride, ++it) {
+        const TileCoord t = tile_coord(p, tile, nkb, CL, rank);
         const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
@@ -452,7 +488,8 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
               acc = 1;
             }
           }
-          umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
+          if (CL > 1) umma_commit_mc(&empty[s], (uint16_t)3);  // both producers refill this stage only when both MMAs are done
+          else umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull[as]);   // accumulator complete
@@ -471,8 +508,8 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
     const bool rmw = (p.epi & LFI_EPI_ACCUM) && p.splitk == 1;
     const bool rmw_pre = (p.epi & LFI_EPI_ACCUM_PRE) != 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const TileCoord t = tile_coord(p, tile, nkb);
+    for (int tile = tile0; tile < ntiles; tile += tstride, ++it) {
+      const TileCoord t = tile_coord(p, tile, nkb, CL, rank);
       const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
       float *C = want_c ? p.C + (size_t)t.b * p.sC : nullptr;
       const float *bias = (p.epi & LFI_EPI_BIAS) ? p.bias + (size_t)t.b * p.sBias : nullptr;
@@ -599,6 +636,7 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_arrive_wait();  // no CTA leaves while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -735,7 +773,11 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   if (g.pOut.hi) p.vec = p.vec && al16(g.pOut.hi) && (!g.pOut.lo || al16(g.pOut.lo)) && g.pOut.ld % 4 == 0 && g.pOut.stride % 4 == 0;
 
   CUtensorMap mA0, mA1, mB0, mB1;
-  const int a_box = A.mn ? BK : BM, b_box = B.mn ? BK : (g.fuse == LFI_FUSE_GRU_FWD ? 64 : p.bn);
+  // cluster pairing: even number of row tiles, a B tile that splits in two halves of whole swizzle atoms / 64-wide chunks
+  static const bool pair_on = env_flag("LFI_GEMM_PAIR", true);
+  const bool pair = pair_on && g.fuse == LFI_FUSE_NONE && p.tiles_m % 2 == 0 && p.bn % 128 == 0 &&
+                    (long)p.tiles_m * p.tiles_n * g.batch * p.splitk >= g_sms;
+  const int a_box = A.mn ? BK : BM, b_box = B.mn ? BK : (g.fuse == LFI_FUSE_GRU_FWD ? 64 : (pair ? p.bn / 2 : p.bn));
   LFI_TRY(make_map(&mA0, A.hi, A.rows, A.cols, A.ldp, A.stride, g.batch, a_box));
   LFI_TRY(make_map(&mB0, B.hi, B.rows, B.cols, B.ldp, B.stride, g.batch, b_box));
   if (nplanes == 2) {
@@ -747,18 +789,31 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   const int smem = p.stages * stage_bytes + fixed;
   static bool attr_set = false;
   if (!attr_set) {
-    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_GRU_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_GRU_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_NONE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_NONE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_GRU_FWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_GRU_BWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
   const long ntiles = tiles * p.splitk;
   const int grid = (int)(ntiles < g_sms ? ntiles : g_sms);
   // request > half of the SM's shared memory so that two CTAs (each wanting all 512 TMEM columns) never share an SM
   const int smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;
-  if (g.fuse == LFI_FUSE_GRU_FWD) gemm_tc_kernel<LFI_FUSE_GRU_FWD><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
-  else if (g.fuse == LFI_FUSE_GRU_BWD) gemm_tc_kernel<LFI_FUSE_GRU_BWD><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
-  else gemm_tc_kernel<LFI_FUSE_NONE><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
+  if (g.fuse == LFI_FUSE_GRU_FWD) gemm_tc_kernel<LFI_FUSE_GRU_FWD, 1><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
+  else if (g.fuse == LFI_FUSE_GRU_BWD) gemm_tc_kernel<LFI_FUSE_GRU_BWD, 1><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
+  else if (pair) {
+    // 2-CTA clusters: the CTAs of a cluster work on vertically adjacent tiles and share the B operand through TMA multicast
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    const long pairs = ntiles / 2;
+    int gp = (int)(pairs < g_sms / 2 ? pairs : g_sms / 2);
+    cfg.gridDim = dim3(2 * gp, 1, 1); cfg.blockDim = dim3(kThreads, 1, 1); cfg.dynamicSmemBytes = smem_req; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    LFI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<LFI_FUSE_NONE, 2>, p, mA0, mA1, mB0, mB1));
+  } else gemm_tc_kernel<LFI_FUSE_NONE, 1><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
   LFI_LAUNCH_CHECK();
   return LFI_OK;
 }
