@@ -1,0 +1,117 @@
+"""GPU tests of the fast paths at BASELINE.json sizes: the stage-pipelined flow core against the general wavefront
+kernels, the tensor-core sampler against the in-kernel fp32 sampler, and size-independent properties (forward ->
+invert round trip, batch-shard equivalence) in the tensor-core modes the bench runs in.  Everything goes through the
+module API -> C ABI; the oracle is only the checker."""
+import os
+
+import pytest
+import torch
+
+from oracle import glow_oracle as O
+from tests.helpers import final_hparams, relerr
+from tests.kat import build_kat_model, kat_batch, oracle_params_from, to_device
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class _env:
+    """Environment switches of the library are read at call time (getenv inside the C ABI)."""
+
+    def __init__(self, **kv):
+        self.kv, self.old = kv, {}
+
+    def __enter__(self):
+        for k, v in self.kv.items():
+            self.old[k] = os.environ.get(k)
+            os.environ[k] = v
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _model(mode):
+    from lets_face_it_b200 import _cabi as cabi
+
+    hp = final_hparams()
+    m = build_kat_model(hp, DEV)
+    m.glow.set_actnorm_init(True)
+    m.gemm_mode = {"fp32": cabi.GEMM_FP32, "bf16x3": cabi.GEMM_BF16X3, "bf16": cabi.GEMM_BF16}[mode]
+    return hp, m
+
+
+def _fwd_bwd(m, batch):
+    m.zero_grad()
+    z_seq, loss, losses = m(batch)
+    loss.backward()
+    g = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    return torch.stack(z_seq).detach().clone(), torch.stack(losses).detach().clone(), g
+
+
+@pytest.mark.parametrize("B", [256, 100])
+def test_pipelined_core_matches_wavefront_kernels(B):
+    """final_model.yaml, T=80: the persistent stage-pipelined core (2-CTA clusters, weights resident in shared memory) and
+    the general wavefront kernels are two schedules of the same arithmetic: z / NLL to 1e-5, gradients to 1e-4 (fp32
+    summation order differs).  B=100 leaves a ragged second tile (36 rows: the second CTA of the cluster owns 4)."""
+    hp, m = _model("fp32")
+    m.train()
+    batch = to_device(kat_batch(hp, B, 80, seed=11), DEV)
+    z1, n1, g1 = _fwd_bwd(m, batch)
+    with _env(LFI_CORE_PIPE="0"):
+        z0, n0, g0 = _fwd_bwd(m, batch)
+    assert relerr(z1, z0) < 1e-5
+    assert relerr(n1, n0) < 1e-5
+    for k in g0:
+        ref = g0[k].double()
+        err = float((g1[k].double() - ref).norm() / ref.norm().clamp_min(1e-30))
+        assert err < 1e-4, (k, err)
+
+
+def test_full_size_roundtrip_and_sharding_in_parity_mode():
+    """BASELINE configs[1] size (B=256, T=80) in the bf16x3 mode the bench runs in: forward -> invert reproduces the input
+    frames (encode / decode round trip through the pipelined core, the fused GRU epilogue, the operand planes and the
+    row-owned inverse kernel), and the batch is separable: the first 128 sequences alone give the same z (what batch
+    sharding over GPUs relies on)."""
+    hp, m = _model("bf16x3")
+    m.eval()
+    batch = to_device(kat_batch(hp, 256, 80, seed=12), DEV)
+    with torch.no_grad():
+        z_seq, loss, losses = m(batch)
+        rec, _ = m.invert(z_seq, batch)
+        half = {k: v[:128].contiguous() for k, v in batch.items()}
+        z_half, _, nll_half = m(half)
+    x = batch["p1_face"][:, 24:].transpose(0, 1)
+    assert relerr(torch.stack(rec), x) < 5e-4
+    assert relerr(torch.stack(z_half), torch.stack(z_seq)[:, :128]) < 1e-5
+    assert relerr(torch.stack(nll_half), torch.stack(losses)[:, :128]) < 1e-5
+    assert torch.isfinite(loss).all()
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 1e-4), ("bf16", 5e-3)])
+def test_tensor_core_sampler_matches_fp32_sampler(mode, tol):
+    """Autoregressive sampling, 200 sequences (ragged tiles) x 40 frames, identical injected noise: per-frame tcgen05
+    conditioning GEMMs + row-owned inverse kernel (tensor-core modes) against the fully in-kernel fp32 sampler."""
+    hp, m = _model("fp32")
+    hy = O.Hyper.from_hparams(hp)
+    m.eval()
+    B, Tg = 200, 40
+    T = hy.start_ts + Tg
+    data = to_device(kat_batch(hp, B, T, seed=13), DEV)
+    data["p1_face"] = torch.zeros(B, hy.start_ts, hy.C, device=DEV)
+    noise = (torch.randn(Tg, B, hy.C, generator=torch.Generator().manual_seed(3)) * 0.7).to(DEV)
+    x32 = m.inference(T, data=data, noise=noise)
+    from lets_face_it_b200 import _cabi as cabi
+
+    m.gemm_mode = {"bf16x3": cabi.GEMM_BF16X3, "bf16": cabi.GEMM_BF16}[mode]
+    xtc = m.inference(T, data=data, noise=noise)
+    assert xtc.shape == (B, Tg, hy.C)
+    assert relerr(xtc, x32) < tol
+    # and against the CPU oracle on a slice of the batch (the oracle is O(minutes) at full size)
+    P = {k: v.detach() for k, v in oracle_params_from(m).items()}
+    sl = {k: v[:8].cpu() for k, v in data.items()}
+    x_ref = O.seq_inference(P, hy, sl, T, noise=noise[:, :8].cpu())
+    assert relerr(xtc[:8], x_ref) < tol
