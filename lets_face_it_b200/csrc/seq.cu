@@ -84,6 +84,8 @@ struct EncWs {
   float *dah32, *dan32;   // fp32 mode: [hist][M][3E], [hist][M][E]
   void *dah_hi, *dah_lo, *dan_hi, *dan_lo;  // planes, same shapes
   void *xg_hi, *xg_lo;    // masked window inputs [hist][M][round_up(dim, 8)]
+  float *xg32;            // the same in fp32 [hist][M][dim] (split source / fp32-mode operand)
+  float *dhe;             // [M][E] running d h of the window recurrence
 };
 
 // A modality's encoder runs on operand planes when every GEMM it issues is taken by the tcgen05 tiles.
@@ -148,6 +150,8 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
       e.dah32 = b.take<float>(h * M * 3 * E);
       e.dan32 = b.take<float>(h * M * E);
     }
+    e.xg32 = b.take<float>(h * M * s->dim[m]);
+    e.dhe = b.take<float>(M * E);
     if (M * 3 * E > ghmax) ghmax = M * 3 * E;
     if (h * M * s->dim[m] > xgmax) xgmax = h * M * s->dim[m];
     if (E > emax) emax = E;
@@ -444,22 +448,23 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   // 4. encoder GRUs, BPTT over the window (models.py:63-64).  Per step only the gate math and dh_prev = dA_h W_hh
   //    run; the gate gradients of all steps are kept so that every weight gradient is ONE long-K GEMM per modality
   //    (reduction over hist x M rows), and the bias gradients are accumulated inside the gate kernel.
-  for (int m = 0; m < LFI_NMOD; ++m) {
+  //    The modalities are independent chains of a latency-bound GEMM and an HBM-bound gate kernel per window step: with
+  //    every operand in plane form (no shared scratch) they run on parallel streams forked from / joined to the caller's.
+  auto enc_bwd = [&](int m, cudaStream_t st) -> int {
     const int hist = s->hist[m], E = s->ehid[m], dim = s->dim[m];
-    if (hist <= 0 || E <= 0) continue;
     EncWs &ew = w.enc[m];
     const bool lo = gemm_mode == LFI_GEMM_BF16X3;
     const int dimp = round_up(dim, 8);
-    LFI_TRY(aux::gather_windows(w.xg, dim, 1, bt->x[m], bt->mask[m], B, T, dim, hist, 1, d.start_ts, Tp, st));
-    if (ew.planes) LFI_TRY(split_to_planes(w.xg, (int)(hist * M), dim, dim, 0, 1, ew.xg_hi, lo ? ew.xg_lo : nullptr, st));
-    LFI_TRY(aux::fill(w.dhe, 0.f, M * E, st));
+    LFI_TRY(aux::gather_windows(ew.xg32, dim, 1, bt->x[m], bt->mask[m], B, T, dim, hist, 1, d.start_ts, Tp, st));
+    if (ew.planes) LFI_TRY(split_to_planes(ew.xg32, (int)(hist * M), dim, dim, 0, 1, ew.xg_hi, lo ? ew.xg_lo : nullptr, st));
+    LFI_TRY(aux::fill(ew.dhe, 0.f, M * E, st));
     const bool fused = ew.planes && (E == 64 || E == 128 || E == 192 || E == 256) && env_flag("LFI_FUSED_GRU_BWD", false);
     for (int sidx = hist - 1; sidx >= 0; --sidx) {
       aux::EncStepBwd2 e;
       memset(&e, 0, sizeof(e));
       e.gates = ew.gates + (size_t)sidx * M * 3 * E; e.ahn = ew.ahn + (size_t)sidx * M * E;
       e.hprev = sidx ? ew.hs + (size_t)(sidx - 1) * M * E : nullptr;
-      e.dh = w.dhe; e.dh_extra = (sidx == hist - 1) ? w.dcond + d.enc_offe[m] : nullptr; e.dh_extra_ld = d.Fe;
+      e.dh = ew.dhe; e.dh_extra = (sidx == hist - 1) ? w.dcond + d.enc_offe[m] : nullptr; e.dh_extra_ld = d.Fe;
       if (ew.planes) {
         e.dah_hi = off16(ew.dah_hi, (size_t)sidx * M * 3 * E); e.dah_lo = lo ? off16(ew.dah_lo, (size_t)sidx * M * 3 * E) : nullptr;
         e.dan_hi = off16(ew.dan_hi, (size_t)sidx * M * E);     e.dan_lo = lo ? off16(ew.dan_lo, (size_t)sidx * M * E) : nullptr;
@@ -469,7 +474,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
       e.gb_ih = g->enc_b_ih[m]; e.gb_hh = g->enc_b_hh[m]; e.M = (int)M; e.E = E;
       if (!fused || sidx == hist - 1) LFI_TRY(aux::enc_gate_bwd2(e, st));
       if (sidx) {  // dh_{s-1} += dA_h W_hh
-        GemmArgs t = gemm_args(0, 0, (int)M, E, 3 * E, e.dah32, 3 * E, p->enc_w_hh[m], E, w.dhe, E, LFI_EPI_ACCUM);
+        GemmArgs t = gemm_args(0, 0, (int)M, E, 3 * E, e.dah32, 3 * E, p->enc_w_hh[m], E, ew.dhe, E, LFI_EPI_ACCUM);
         if (ew.planes) { t.pA = plane_ref(e.dah_hi, e.dah_lo, 3 * E); t.pB = plane_ref(ew.whh_hi, ew.whh_lo, E); }
         if (fused) {  // ... and the gate backward of step s-1 in the same launch
           t.C = nullptr; t.epi = 0; t.fuse = LFI_FUSE_GRU_BWD;
@@ -477,7 +482,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
           q.E = E;
           q.bgates = ew.gates + (size_t)(sidx - 1) * M * 3 * E; q.bahn = ew.ahn + (size_t)(sidx - 1) * M * E;
           q.bhprev = sidx - 1 > 0 ? ew.hs + (size_t)(sidx - 2) * M * E : nullptr;
-          q.dh = w.dhe;
+          q.dh = ew.dhe;
           q.dah_hi = off16(ew.dah_hi, (size_t)(sidx - 1) * M * 3 * E); q.dah_lo = lo ? off16(ew.dah_lo, (size_t)(sidx - 1) * M * 3 * E) : nullptr;
           q.dan_hi = off16(ew.dan_hi, (size_t)(sidx - 1) * M * E);     q.dan_lo = lo ? off16(ew.dan_lo, (size_t)(sidx - 1) * M * E) : nullptr;
           q.gb_ih = g->enc_b_ih[m]; q.gb_hh = g->enc_b_hh[m];
@@ -492,15 +497,42 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
       LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
     }
     {  // dW_ih rows [0,2E) += dA_h[:, :2E]^T x  (r, u blocks coincide with the i-side gradients); rows [2E,3E) += dA_n^T x
-      GemmArgs q = gemm_args(1, 0, 2 * E, dim, Kall, ew.dah32, 3 * E, w.xg, dim, g->enc_w_ih[m], dim, LFI_EPI_ACCUM);
+      GemmArgs q = gemm_args(1, 0, 2 * E, dim, Kall, ew.dah32, 3 * E, ew.xg32, dim, g->enc_w_ih[m], dim, LFI_EPI_ACCUM);
       if (ew.planes) { q.pA = plane_ref(ew.dah_hi, ew.dah_lo, 3 * E); q.pB = plane_ref(ew.xg_hi, ew.xg_lo, dimp); }
       LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
-      GemmArgs r = gemm_args(1, 0, E, dim, Kall, ew.dan32, E, w.xg, dim, g->enc_w_ih[m] + (size_t)2 * E * dim, dim, LFI_EPI_ACCUM);
+      GemmArgs r = gemm_args(1, 0, E, dim, Kall, ew.dan32, E, ew.xg32, dim, g->enc_w_ih[m] + (size_t)2 * E * dim, dim, LFI_EPI_ACCUM);
       if (ew.planes) { r.pA = plane_ref(ew.dan_hi, ew.dan_lo, E); r.pB = plane_ref(ew.xg_hi, ew.xg_lo, dimp); }
       LFI_TRY(gemm_dispatch(gemm_mode, r, gws, gws_bytes, st));
     }
+    return LFI_OK;
+  };
+  int mods[LFI_NMOD], nmods = 0;
+  bool all_planes = true;
+  for (int m = 0; m < LFI_NMOD; ++m)
+    if (s->hist[m] > 0 && s->ehid[m] > 0) { mods[nmods++] = m; all_planes = all_planes && w.enc[m].planes; }
+  static cudaStream_t side[LFI_NMOD] = {nullptr, nullptr, nullptr, nullptr};
+  static cudaEvent_t ev_fork = nullptr, ev_join[LFI_NMOD] = {nullptr, nullptr, nullptr, nullptr};
+  const bool par = nmods > 1 && all_planes && env_flag("LFI_ENC_STREAMS", true);
+  if (!par) {
+    for (int i = 0; i < nmods; ++i) LFI_TRY(enc_bwd(mods[i], st));
+    return LFI_OK;
   }
-  return LFI_OK;
+  if (!ev_fork) {
+    LFI_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < LFI_NMOD; ++i) {
+      LFI_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+      LFI_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+    }
+  }
+  LFI_CUDA(cudaEventRecord(ev_fork, st));
+  for (int i = 1; i < nmods; ++i) LFI_CUDA(cudaStreamWaitEvent(side[i], ev_fork, 0));
+  int rc = LFI_OK;
+  for (int i = 0; i < nmods && rc == LFI_OK; ++i) rc = enc_bwd(mods[i], i == 0 ? st : side[i]);
+  for (int i = 1; i < nmods; ++i) {  // always join, also on error
+    cudaEventRecord(ev_join[i], side[i]);
+    cudaStreamWaitEvent(st, ev_join[i], 0);
+  }
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
