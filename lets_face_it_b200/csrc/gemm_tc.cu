@@ -53,6 +53,8 @@ struct Params {
   // optional bf16 plane output of the final value (hi, and lo = bf16(v - hi) when o_lo != nullptr); C may then be null
   __nv_bfloat16 *o_hi, *o_lo; int ldo; long sO;
   int vec;  // all fp32 pointers / pitches allow 128-bit accesses
+  const __nv_bfloat16 *auxp; int ldauxp; long sAuxp;  // LeakyReLU' mask from the sign of a bf16 plane
+  float *colsum; long sColsum;                          // += column sums of the final values
   int fuse;     // LFI_FUSE_*
   int cond_vec; // fused GRU forward: the cond slice allows 128-bit stores
   GruEpi gru;
@@ -103,17 +105,28 @@ __device__ __forceinline__ void tma_load_3d(void *smem, const CUtensorMap *map, 
       : "memory");
 }
 
-// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, each of which also gets the
-// complete_tx on its own barrier at the same offset
-__device__ __forceinline__ void tma_load_3d_mc(void *smem, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, uint16_t mask) {
+// ---- cta_group::2 (CTA pair) variants -----------------------------------------------------------------
+// The two CTAs of a cluster sit on the two SMs of a TPC and execute ONE tcgen05.mma over a 256-row tile: each CTA
+// stages its own 128 rows of A and HALF of the B tile, the tensor cores of both SMs read both halves, each CTA's TMEM
+// receives its 128 accumulator rows.  Only the leader (cluster rank 0) issues MMAs; TMA loads of both CTAs signal the
+// LEADER's full barrier, MMA completion is committed to the barriers of both CTAs.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void *smem, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"((uint64_t)map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {  // arrives on the same barrier in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void cluster_arrive_wait() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -132,6 +145,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -177,12 +198,13 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
 
 struct TileCoord { int b, m0, n0, kb0, kb1; };
 
-// CL = 2: the two CTAs of a cluster take the row tiles 2i and 2i+1 of the same column tile and share its B operand
+// CL = 2: the two CTAs of a pair take the row tiles 2i and 2i+1 of the same column tile (a 256-row UMMA tile); with an odd
+// number of row tiles the last pair's second half lies outside the matrix (TMA zero fill, epilogue row guard)
 __device__ __forceinline__ TileCoord tile_coord(const Params &p, int tile, int nkb, int CL = 1, int rank = 0) {
   // n fastest, then m, then split-k, then batch: CTAs running side by side share the A rows through L2
   TileCoord t;
   const int tn = tile % p.tiles_n; tile /= p.tiles_n;
-  const int tmm = p.tiles_m / CL;
+  const int tmm = (p.tiles_m + CL - 1) / CL;
   const int tm = (tile % tmm) * CL + rank; tile /= tmm;
   const int sk = tile % p.splitk;  tile /= p.splitk;
   t.b = tile; t.m0 = tm * BM; t.n0 = tn * p.bn;
@@ -384,7 +406,7 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
   // carve-up: [stages][A planes | B planes] | epilogue staging | barriers | tmem address
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t a_plane = BM * BK * 2;            // 16 KB
-  const uint32_t b_plane = (uint32_t)p.bn * BK * 2;
+  const uint32_t b_plane = (uint32_t)(p.bn / CL) * BK * 2;  // CTA pair: each CTA stages half of the B tile
   const uint32_t stage_bytes = p.nplanes * (a_plane + b_plane);
   float *epi_stage = (float *)(smem + (size_t)p.stages * stage_bytes);
   uint64_t *bars = (uint64_t *)((uint8_t *)epi_stage + kEpiBytes);
@@ -393,22 +415,27 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.K + BK - 1) / BK;
-  const int ntiles = (p.tiles_m / CL) * p.tiles_n * p.splitk * p.batch;  // per cluster
+  const int ntiles = ((p.tiles_m + CL - 1) / CL) * p.tiles_n * p.splitk * p.batch;  // per cluster
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
   const int tile0 = blockIdx.x / CL, tstride = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kEpiWarps); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], CL * kEpiWarps); }  // pair: the leader's collects both epilogues
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CL == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (CL > 1) cluster_arrive_wait();  // the peer's barriers are initialised before anything is multicast into them
+  if (CL > 1) cluster_arrive_wait();  // the peer's barriers are initialised before anything is signalled into them
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -419,14 +446,21 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
         const TileCoord t = tile_coord(p, tile, nkb, CL, rank);
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], stage_bytes);
+          if (CL == 1 || rank == 0) mbar_expect_tx(&full[s], CL * stage_bytes);  // pair: both CTAs' loads land on the leader's barrier
+          const uint32_t fbar = CL > 1 ? mapa_u32(smem_u32(&full[s]), 0) : 0;
           uint8_t *sa = smem + (size_t)s * stage_bytes;
           uint8_t *sb = sa + p.nplanes * a_plane;
           const int k0 = kb * BK;
           for (int pl = 0; pl < p.nplanes; ++pl) {
             const CUtensorMap *ma = pl ? &mapA1 : &mapA0;
             const CUtensorMap *mb = pl ? &mapB1 : &mapB0;
-            if (!p.a_mn) {
+            if constexpr (CL == 2) {
+              if (!p.a_mn) {
+                tma_load_3d_2sm(sa + pl * a_plane, ma, fbar, k0, t.m0, t.b);
+              } else {
+                for (int j = 0; j < BM / 64; ++j) tma_load_3d_2sm(sa + pl * a_plane + j * (BK * 128), ma, fbar, t.m0 + 64 * j, k0, t.b);
+              }
+            } else if (!p.a_mn) {
               tma_load_3d(sa + pl * a_plane, ma, &full[s], k0, t.m0, t.b);
             } else {
               for (int j = 0; j < BM / 64; ++j) tma_load_3d(sa + pl * a_plane + j * (BK * 128), ma, &full[s], t.m0 + 64 * j, k0, t.b);
@@ -435,15 +469,13 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
               // 64 hidden units x (r, u, n): three 64-row boxes of W_hh, 8-row swizzle atoms stay contiguous
               const int u0 = (t.n0 / 192) * 64;
               for (int g = 0; g < 3; ++g) tma_load_3d(sb + pl * b_plane + g * (64 * 128), mb, &full[s], k0, g * p.gru.E + u0, t.b);
-            } else if (CL > 1) {
-              // this CTA fetches its half of the shared B tile and multicasts it to both CTAs of the cluster
+            } else if constexpr (CL == 2) {
+              // this CTA stages its half of the B tile: columns [n0 + rank * bn/2, + bn/2)
+              const int half = p.bn / 2;
               if (!p.b_mn) {
-                const int half_rows = p.bn / 2;
-                tma_load_3d_mc(sb + pl * b_plane + rank * half_rows * 128, mb, &full[s], k0, t.n0 + rank * half_rows, t.b, (uint16_t)3);
+                tma_load_3d_2sm(sb + pl * b_plane, mb, fbar, k0, t.n0 + rank * half, t.b);
               } else {
-                const int hc = p.bn / 128;  // 64-wide chunks per CTA
-                for (int j = rank * hc; j < (rank + 1) * hc; ++j)
-                  tma_load_3d_mc(sb + pl * b_plane + j * (BK * 128), mb, &full[s], t.n0 + 64 * j, k0, t.b, (uint16_t)3);
+                for (int j = 0; j < half / 64; ++j) tma_load_3d_2sm(sb + pl * b_plane + j * (BK * 128), mb, fbar, t.n0 + rank * half + 64 * j, k0, t.b);
               }
             } else if (!p.b_mn) {
               tma_load_3d(sb + pl * b_plane, mb, &full[s], k0, t.n0, t.b);
@@ -457,9 +489,9 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                             ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((CL * BM) >> 4) << 24);
       const uint32_t a_lbo = p.a_mn ? BK * 128 : 0, b_lbo = p.b_mn ? BK * 128 : 0;
       const uint32_t a_adv = p.a_mn ? (UK * 128) >> 4 : (UK * 2) >> 4;  // descriptor address step per UMMA_K
       const uint32_t b_adv = p.b_mn ? (UK * 128) >> 4 : (UK * 2) >> 4;
@@ -484,15 +516,17 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
             const uint64_t bd = make_sdesc(sb + pb * b_plane, b_lbo, 1024);
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {
-              umma_bf16(d_tmem, ad + (uint64_t)(k * a_adv), bd + (uint64_t)(k * b_adv), idesc, acc);
+              if constexpr (CL == 2) umma_bf16_2sm(d_tmem, ad + (uint64_t)(k * a_adv), bd + (uint64_t)(k * b_adv), idesc, acc);
+              else umma_bf16(d_tmem, ad + (uint64_t)(k * a_adv), bd + (uint64_t)(k * b_adv), idesc, acc);
               acc = 1;
             }
           }
-          if (CL > 1) umma_commit_mc(&empty[s], (uint16_t)3);  // both producers refill this stage only when both MMAs are done
-          else umma_commit(&empty[s]);  // frees the stage once the MMAs above have read it
+          if constexpr (CL == 2) umma_commit_2sm(&empty[s]);  // frees the stage in both CTAs once the MMAs above have read it
+          else umma_commit(&empty[s]);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[as]);   // accumulator complete
+        if constexpr (CL == 2) umma_commit_2sm(&tfull[as]);  // accumulator complete (in both CTAs' TMEM)
+        else umma_commit(&tfull[as]);
       }
     }
   } else {
@@ -513,7 +547,9 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
       const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
       float *C = want_c ? p.C + (size_t)t.b * p.sC : nullptr;
       const float *bias = (p.epi & LFI_EPI_BIAS) ? p.bias + (size_t)t.b * p.sBias : nullptr;
-      const float *aux = (p.epi & LFI_EPI_LRELU_BWD) ? p.aux + (size_t)t.b * p.sAux : nullptr;
+      const float *aux = ((p.epi & LFI_EPI_LRELU_BWD) && !p.auxp) ? p.aux + (size_t)t.b * p.sAux : nullptr;
+      const __nv_bfloat16 *auxp = ((p.epi & LFI_EPI_LRELU_BWD) && p.auxp) ? p.auxp + (size_t)t.b * p.sAuxp : nullptr;
+      float *colsum = p.colsum ? p.colsum + (size_t)t.b * p.sColsum : nullptr;
       __nv_bfloat16 *ohi = p.o_hi ? p.o_hi + (size_t)t.b * p.sO : nullptr;
       __nv_bfloat16 *olo = p.o_lo ? p.o_lo + (size_t)t.b * p.sO : nullptr;
       const bool has_work = t.kb1 > t.kb0;
@@ -541,7 +577,18 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
               const int m = mrow0 + rr + 8 * i;
               pre[i] = m < p.M ? *reinterpret_cast<const float4 *>(src + (size_t)m * ld + n) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+          } else if (ncol_ok && auxp) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int m = mrow0 + rr + 8 * i;
+              uint2 raw = make_uint2(0u, 0u);
+              if (m < p.M) raw = *reinterpret_cast<const uint2 *>(auxp + (size_t)m * p.ldauxp + n);
+              // bf16 -> fp32 keeps the sign: value bits in the upper half of the word
+              pre[i] = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u), __uint_as_float(raw.y << 16),
+                                   __uint_as_float(raw.y & 0xffff0000u));
+            }
           }
+          float cs[4] = {0.f, 0.f, 0.f, 0.f};
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (bias && ncol_ok) bv = *reinterpret_cast<const float4 *>(bias + n);
           if (!waited) { mbar_wait(&tfull[as], aph); tc_fence_after(); waited = true; }
@@ -568,9 +615,10 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
                 if (rmw_pre) y += a4[e];
                 y += b4[e];
                 if (p.epi & LFI_EPI_LRELU) y = y > 0.f ? y : kLeaky * y;
-                if (aux) y *= (a4[e] > 0.f ? 1.f : kLeaky);
+                if (aux || auxp) y *= (a4[e] > 0.f ? 1.f : kLeaky);
                 if (rmw) y += a4[e];
                 x[e] = y;
+                cs[e] += y;
               }
               if (want_c) {
                 float *dst = C + (size_t)m * p.ldc + n;
@@ -594,6 +642,18 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
               }
             }
           }
+          if (colsum) {  // rows of this pass: butterfly over the eight row lanes, one atomic per column
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 1);
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 2);
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 4);
+            }
+            if (rr == 0 && ncol_ok) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) atomicAdd(colsum + n + e, cs[e]);
+            }
+          }
           __syncwarp();
         } else {
           // generic path (odd pitches / unaligned bases): thread = row, scalar accesses
@@ -612,6 +672,8 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
               if (bias) y += bias[n];
               if (p.epi & LFI_EPI_LRELU) y = y > 0.f ? y : kLeaky * y;
               if (aux) y *= (aux[(size_t)m * p.ldaux + n] > 0.f ? 1.f : kLeaky);
+              if (auxp) y *= (__bfloat162float(auxp[(size_t)m * p.ldauxp + n]) > 0.f ? 1.f : kLeaky);
+              if (colsum) atomicAdd(colsum + n, y);
               if (want_c) {
                 float *dst = C + (size_t)m * p.ldc + n;
                 if (p.splitk > 1) atomicAdd(dst, y);
@@ -630,16 +692,20 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
       if (!waited) { mbar_wait(&tfull[as], aph); tc_fence_after(); }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if (CL == 1 || rank == 0) mbar_arrive(&tempty[as]);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0));
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_arrive_wait();  // no CTA leaves while its peer may still multicast into it
+  if (CL > 1) cluster_arrive_wait();  // no CTA leaves while its peer may still read its operands / signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if constexpr (CL == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -739,20 +805,34 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
     p.bn = g.N;
   }
   p.nplanes = nplanes; p.a_mn = A.mn; p.b_mn = B.mn;
-  p.tiles_m = (g.M + BM - 1) / BM; p.tiles_n = (g.N + p.bn - 1) / p.bn;
-  const int stage_bytes = nplanes * (BM * BK * 2 + p.bn * BK * 2);
-  const int fixed = kEpiBytes + (2 * kMaxStages + 4) * 8 + 16 + 1024;
-  p.stages = (kSmemLimit - fixed) / stage_bytes;
-  if (p.stages > kMaxStages) p.stages = kMaxStages;
-  LFI_REQUIRE(p.stages >= 2, LFI_ERR_SHAPE, "gemm_tc: tile does not fit shared memory");
-  const int nkb = (g.K + BK - 1) / BK;
   if (!g_sms) {
     int dev = 0;
     LFI_CUDA(cudaGetDevice(&dev));
     LFI_CUDA(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  // CTA pairs (cta_group::2, 256-row UMMA tiles): each CTA stages half of the B tile, which halves the operand bytes an SM
+  // pulls from L2 per MMA cycle - the bound of the 128-row tiles in the split-bf16 mode (64 B/clk/SM needed, ~43 available).
+  // Needs a B tile that splits into two halves of whole swizzle atoms (K-major) / 64-wide chunks (MN-major) and enough
+  // tiles to fill the machine with pairs.
+  static const bool pair_on = env_flag("LFI_GEMM_PAIR", true);
+  bool pair = false;
+  if (pair_on && g.fuse == LFI_FUSE_NONE) {
+    int bn2 = p.bn;
+    if (B.mn && bn2 % 128 != 0) bn2 = g.N > 128 ? 256 : 128;
+    if (!B.mn && bn2 % 16 != 0) bn2 = round_up(bn2, 16);
+    const long ptiles = (long)(((g.M + BM - 1) / BM + 1) / 2) * ((g.N + bn2 - 1) / bn2) * g.batch;
+    if (g.M > BM && ptiles >= g_sms / 2) { pair = true; p.bn = bn2; }
+  }
+  const int CL = pair ? 2 : 1;
+  p.tiles_m = (g.M + BM - 1) / BM; p.tiles_n = (g.N + p.bn - 1) / p.bn;
+  const int stage_bytes = nplanes * (BM * BK * 2 + (p.bn / CL) * BK * 2);  // per CTA
+  const int fixed = kEpiBytes + (2 * kMaxStages + 4) * 8 + 16 + 1024;
+  p.stages = (kSmemLimit - fixed) / stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  LFI_REQUIRE(p.stages >= 2, LFI_ERR_SHAPE, "gemm_tc: tile does not fit shared memory");
+  const int nkb = (g.K + BK - 1) / BK;
   p.splitk = 1;
-  const long tiles = (long)p.tiles_m * p.tiles_n * g.batch;
+  const long tiles = (long)((p.tiles_m + CL - 1) / CL) * CL * p.tiles_n * g.batch;  // CTA tiles (pairs: incl. an empty half)
   if (g.epi == LFI_EPI_ACCUM && tiles * 2 <= g_sms && nkb >= 16) {
     int sk = (int)((g_sms + tiles - 1) / tiles);
     if (sk > nkb / 8) sk = nkb / 8;
@@ -769,14 +849,13 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   p.vec = g.N % 4 == 0;
   if (g.C) p.vec = p.vec && al16(g.C) && g.ldc % 4 == 0 && g.sC % 4 == 0;
   if (g.epi & LFI_EPI_BIAS) p.vec = p.vec && al16(g.bias) && g.sBias % 4 == 0;
-  if (g.epi & LFI_EPI_LRELU_BWD) p.vec = p.vec && al16(g.aux) && g.ldaux % 4 == 0 && g.sAux % 4 == 0;
+  p.auxp = (const __nv_bfloat16 *)g.auxp; p.ldauxp = g.ldauxp; p.sAuxp = g.sAuxp; p.colsum = g.colsum; p.sColsum = g.sColsum;
+  if ((g.epi & LFI_EPI_LRELU_BWD) && !g.auxp) p.vec = p.vec && al16(g.aux) && g.ldaux % 4 == 0 && g.sAux % 4 == 0;
+  if ((g.epi & LFI_EPI_LRELU_BWD) && g.auxp) p.vec = p.vec && (((uintptr_t)g.auxp & 7) == 0) && g.ldauxp % 4 == 0 && g.sAuxp % 4 == 0;
+  if (g.colsum) p.vec = p.vec && g.sColsum % 4 == 0;
   if (g.pOut.hi) p.vec = p.vec && al16(g.pOut.hi) && (!g.pOut.lo || al16(g.pOut.lo)) && g.pOut.ld % 4 == 0 && g.pOut.stride % 4 == 0;
 
   CUtensorMap mA0, mA1, mB0, mB1;
-  // cluster pairing: even number of row tiles, a B tile that splits in two halves of whole swizzle atoms / 64-wide chunks
-  static const bool pair_on = env_flag("LFI_GEMM_PAIR", true);
-  const bool pair = pair_on && g.fuse == LFI_FUSE_NONE && p.tiles_m % 2 == 0 && p.bn % 128 == 0 &&
-                    (long)p.tiles_m * p.tiles_n * g.batch * p.splitk >= g_sms;
   const int a_box = A.mn ? BK : BM, b_box = B.mn ? BK : (g.fuse == LFI_FUSE_GRU_FWD ? 64 : (pair ? p.bn / 2 : p.bn));
   LFI_TRY(make_map(&mA0, A.hi, A.rows, A.cols, A.ldp, A.stride, g.batch, a_box));
   LFI_TRY(make_map(&mB0, B.hi, B.rows, B.cols, B.ldp, B.stride, g.batch, b_box));
@@ -802,7 +881,7 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   if (g.fuse == LFI_FUSE_GRU_FWD) gemm_tc_kernel<LFI_FUSE_GRU_FWD, 1><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
   else if (g.fuse == LFI_FUSE_GRU_BWD) gemm_tc_kernel<LFI_FUSE_GRU_BWD, 1><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
   else if (pair) {
-    // 2-CTA clusters: the CTAs of a cluster work on vertically adjacent tiles and share the B operand through TMA multicast
+    // CTA pairs: one 256-row cta_group::2 tile per cluster
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     const long pairs = ntiles / 2;
@@ -859,7 +938,7 @@ int gemm_tc(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t
   LFI_REQUIRE((g.A || g.pA.hi) && (g.B || g.pB.hi) && (g.C || g.pOut.hi || g.fuse), LFI_ERR_ARG, "gemm: null operand");
   LFI_REQUIRE(nplanes == 1 || ((!g.pA.hi || g.pA.lo) && (!g.pB.hi || g.pB.lo)), LFI_ERR_ARG, "gemm: split-bf16 mode needs lo planes");
   LFI_REQUIRE(!(g.epi & LFI_EPI_BIAS) || g.bias, LFI_ERR_ARG, "gemm: bias epilogue without bias");
-  LFI_REQUIRE(!(g.epi & LFI_EPI_LRELU_BWD) || g.aux, LFI_ERR_ARG, "gemm: lrelu-bwd epilogue without aux");
+  LFI_REQUIRE(!(g.epi & LFI_EPI_LRELU_BWD) || g.aux || g.auxp, LFI_ERR_ARG, "gemm: lrelu-bwd epilogue without aux");
   // A: transA = 0 -> stored [M, K] (K-major); 1 -> stored [K, M] (MN-major).  B: transB = 1 -> [N, K] (K-major); 0 -> [K, N] (MN-major)
   tc::Operand A, B;
   A.mn = g.transA ? 1 : 0; A.rows = g.transA ? g.K : g.M; A.cols = g.transA ? g.M : g.K;

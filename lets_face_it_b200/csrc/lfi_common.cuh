@@ -162,6 +162,10 @@ struct GemmArgs {
   PlaneRef pOut;    // hi != nullptr: also emit the result as bf16 planes (C may then be null); tensor-core modes only
   int fuse;         // LFI_FUSE_*: replaces the generic epilogue (operands must be planes; tensor-core modes only)
   GruEpi gru;
+  // tensor-core modes only: LeakyReLU' mask taken from the sign of a bf16 plane (instead of the fp32 `aux`), and column sums
+  // of the final values accumulated into colsum[n] (bias gradients without a second pass over the output)
+  const void *auxp; int ldauxp; long sAuxp;
+  float *colsum; long sColsum;
 };
 int gemm_simt(const GemmArgs &g, cudaStream_t st);
 int gemm_dispatch(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st);

@@ -122,8 +122,10 @@ static bool core_planes_ok(const Dims &d, int mode) {
 static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode, void *ws, TrainWs *w) {
   Bump b(ws, 0);
   const size_t Tp = T - d.start_ts, M = Tp * B, K = d.K;
+  w->cp = core_planes_ok(d, mode); w->cp_lo = mode == LFI_GEMM_BF16X3;
   w->cond = b.take<float>(M * d.Fe);
-  w->Cact = b.take<float>(M * K * d.D);
+  // operand-plane mode: the cond_transform activations and their gradients exist as bf16 planes only
+  w->Cact = w->cp ? nullptr : b.take<float>(M * K * d.D);
   w->G = b.take<float>(M * K * d.GH);
   w->ld = b.take<float>(M);
   w->flags = b.take<int>(kFlagInts);
@@ -174,13 +176,12 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
   w->dAh = b.take<float>(cells * d.GH);
   w->dO = b.take<float>(cells * d.Co);
   w->dzf = b.take<float>(cells * d.C);
-  w->dC = b.take<float>(M * K * d.D);
+  w->dC = w->cp ? nullptr : b.take<float>(M * K * d.D);
   w->dcond = b.take<float>(M * d.Fe);
   w->dWcF = b.take<float>(K * d.D * d.Fe);
   w->xg = b.take<float>(xgmax);
   w->dhe = b.take<float>(M * emax);
   w->dai = nullptr; w->dah = nullptr;
-  w->cp = core_planes_ok(d, mode); w->cp_lo = mode == LFI_GEMM_BF16X3;
   if (w->cp) {
     auto two = [&](void *&hi, void *&lo_, size_t n) { hi = take_bf16(b, n); lo_ = w->cp_lo ? take_bf16(b, n) : nullptr; };
     two(w->cact_hi, w->cact_lo, M * K * d.D);
@@ -268,7 +269,7 @@ static int cond_to_gates(const Dims &d, const lfi_params *p, const float *WcF, c
                          void *cact_lo = nullptr) {
   const int K = d.K, D = d.D, GH = d.GH, In = d.Ci + D;
   GemmArgs g = gemm_args(0, 1, (int)M, K * D, d.Fe, cond, d.Fe, WcF, d.Fe, Cact, K * D, LFI_EPI_BIAS | LFI_EPI_LRELU, p->bc);
-  if (cact_hi) g.pOut = plane_ref(cact_hi, cact_lo, K * D);  // the activations leave the epilogue as operand planes too
+  if (cact_hi) { g.pOut = plane_ref(cact_hi, cact_lo, K * D); g.C = nullptr; }  // the activations leave the epilogue as operand planes only
   LFI_TRY(gemm_dispatch(mode, g, gws, gws_bytes, st));
   GemmArgs h = gemm_args(0, 1, (int)M, GH, D, Cact, K * D, p->w_ih + d.Ci, In, G, K * GH, LFI_EPI_BIAS, p->b_ih);
   if (cact_hi) h.pA = plane_ref(cact_hi, cact_lo, K * D, D);
@@ -426,9 +427,13 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   {
     GemmArgs q = gemm_args(0, 0, (int)M, D, GH, w.dG, K * GH, p->w_ih + Ci, In, w.dC, K * D, LFI_EPI_LRELU_BWD);
     q.batch = K; q.sA = GH; q.sB = (long)GH * In; q.sC = D; q.aux = w.Cact; q.ldaux = K * D; q.sAux = D;
-    if (w.cp) { q.pA = pdG; q.pOut = plane_ref(w.dC_hi, w.dC_lo, K * D, D); }
+    if (w.cp) {  // planes in, planes out; LeakyReLU' from the sign of the activation plane; d b_c reduced in the epilogue
+      q.pA = pdG; q.pOut = plane_ref(w.dC_hi, w.dC_lo, K * D, D); q.C = nullptr;
+      q.aux = nullptr; q.auxp = w.cact_hi; q.ldauxp = K * D; q.sAuxp = D;
+      q.colsum = g->bc; q.sColsum = D;
+    }
     LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
-    LFI_TRY(aux::colsum(g->bc, w.dC, K * D, (int)M, K * D, 1.0f, st));
+    if (!w.cp) LFI_TRY(aux::colsum(g->bc, w.dC, K * D, (int)M, K * D, 1.0f, st));
     GemmArgs r = gemm_args(1, 0, K * D, d.Fe, (int)M, w.dC, K * D, w.cond, d.Fe, w.dWcF, d.Fe, 0);
     if (w.cp) r.pA = plane_ref(w.dC_hi, w.dC_lo, K * D);
     LFI_TRY(gemm_dispatch(gemm_mode, r, gws, gws_bytes, st));

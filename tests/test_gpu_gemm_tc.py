@@ -62,6 +62,10 @@ SHAPES = [
     (777, 920, 333, 2),
     (64, 72, 4000, 1),      # long reduction, tiny output
     (4096, 1024, 920, 1),   # cond_transform slice
+    # CTA-pair (cta_group::2, 256-row tiles) path: enough tiles to fill the machine with pairs
+    (9000, 1024, 300, 1),   # odd number of row tiles: the last pair's second half is outside the matrix
+    (1000, 384, 512, 16),   # batched gate-ih shape, bn = 192 split in two 96-column halves
+    (8192, 920, 520, 1),    # ragged N on 256-column tiles
 ]
 
 
