@@ -39,6 +39,9 @@ struct FwdArgs {
   // tensor-core modes, stage-pipelined kernel only: bf16 operand planes (hi, lo = bf16(v - hi); lo nullable) of the stash
   // entries the weight-gradient GEMMs contract over, written next to the fp32 stash
   void *py_hi, *py_lo, *pzf_hi, *pzf_lo, *ph_hi, *ph_lo;
+  // 1: st_gates / st_ahn / st_h use the tiled layout of the tensor-core pipeline (core_pipe.cuh: stash_tiled_off), which makes
+  // the thread-per-sequence stores of that kernel contiguous; the backward pipeline reads the same layout
+  int stash_tiled;
 };
 
 struct InvArgs {
@@ -79,6 +82,7 @@ struct BwdArgs {
   // operand planes (same geometry as dG / dAh / dO / dzf, which may then be nullptr) and b_ih is reduced in-kernel
   void *pdG_hi, *pdG_lo, *pdAh_hi, *pdAh_lo, *pdO_hi, *pdO_lo, *pdzf_hi, *pdzf_lo;
   float *g_b_ih;
+  int stash_tiled;  // st.gates / st.ahn / st.h in the tiled layout (see FwdArgs)
 };
 
 int fwd_smem_bytes(const Dims &d, int R);

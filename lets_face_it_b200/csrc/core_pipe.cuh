@@ -65,10 +65,21 @@ __device__ __forceinline__ void put_plane2(void *hi, void *lo, size_t idx, float
   if (lo) *reinterpret_cast<__nv_bfloat162 *>((__nv_bfloat16 *)lo + idx) = __floats2bfloat162_rn(v0 - __low2float(h), v1 - __high2float(h));
 }
 
+// Tiled stash (gates / ahn / h) shared by the tensor-core forward pipeline and the backward pipeline:
+//   [cell][tile of 64 sequences][CTA c][group hs of 16 hidden units][array][float4 i of the group][64 sequences][4 floats]
+// (narr = 3 arrays r, u, n for the gates, 1 for ahn and h).  A warp of the forward kernel holds 32 consecutive sequences, one
+// per lane, so each of its stores covers 512 contiguous bytes.  Element (sequence row, unit 64c + 16hs + 4i + e): + 4*row + e.
+__host__ __device__ inline size_t stash_tiled_off(size_t cell, int ntiles, int tile, int c, int hs, int narr, int arr, int i) {
+  return (((((cell * ntiles + tile) * 2 + c) * 4 + hs) * narr + arr) * 4 + i) * 256;
+}
+
 bool pipe_supported(const Dims &d, int nk, bool bwd);
 int pipe_bwd_smem_bytes(const Dims &d);
 int launch_fwd_pipe(const FwdArgs &a, cudaStream_t st);
 int launch_bwd_pipe(const BwdArgs &a, cudaStream_t st);
+// tensor-core variants (core_pipe_fwd_tc.cu): gate products as tcgen05.mma on split-bf16 operands, tensor-core GEMM modes only
+bool pipe_tc_supported(const Dims &d, int nk);
+int launch_fwd_pipe_tc(const FwdArgs &a, cudaStream_t st);
 
 }  // namespace core
 }  // namespace lfi

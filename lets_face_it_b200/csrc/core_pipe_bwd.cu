@@ -118,6 +118,24 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
       float2 pg[8][3], pa[8], ph[8];
       {
         const size_t rb = cell * B + row0 + 8 * rg;
+        if (a.stash_tiled) {  // layout of the tensor-core forward pipeline (core_pipe.cuh: stash_tiled_off)
+          const int hs = u0 >> 4, i4 = (u0 & 15) >> 2, eo = (u0 & 3) + 4 * (8 * rg);
+          const float *gq = a.st.gates + stash_tiled_off(cell, ntiles, tile, c, hs, 3, 0, i4) + eo;
+          const float *aq = a.st.ahn + stash_tiled_off(cell, ntiles, tile, c, hs, 1, 0, i4) + eo;
+          const float *hq = a.st.h + stash_tiled_off(cell - (t > 0 ? 1 : 0), ntiles, tile, c, hs, 1, 0, i4) + eo;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if (8 * rg + r < nrows) {
+              pg[r][0] = __ldg(reinterpret_cast<const float2 *>(gq + 4 * r));
+              pg[r][1] = __ldg(reinterpret_cast<const float2 *>(gq + 1024 + 4 * r));
+              pg[r][2] = __ldg(reinterpret_cast<const float2 *>(gq + 2048 + 4 * r));
+              pa[r] = __ldg(reinterpret_cast<const float2 *>(aq + 4 * r));
+              ph[r] = t > 0 ? __ldg(reinterpret_cast<const float2 *>(hq + 4 * r)) : make_float2(0.f, 0.f);
+            } else {
+              pg[r][0] = pg[r][1] = pg[r][2] = pa[r] = ph[r] = make_float2(0.f, 0.f);
+            }
+          }
+        } else
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           if (8 * rg + r < nrows) {

@@ -367,6 +367,7 @@ bool pipe_supported(const Dims &d, int nk, bool bwd) {
 
 int launch_fwd_pipe(const FwdArgs &a, cudaStream_t st) {
   const int nk = a.k_last - a.k_first + 1;
+  if (a.stash_tiled) return launch_fwd_pipe_tc(a, st);  // tensor-core GEMM modes (the caller checked pipe_tc_supported)
   const int bytes = plan_pipe(a.d).total * (int)sizeof(float);
   const int ntiles = (a.B + PR - 1) / PR;
   int P = sm_count() / (2 * nk);

@@ -108,6 +108,7 @@ struct TrainWs {
   // tensor-core modes with the stage-pipelined core: GEMM operands of the flow-step contractions live as bf16 planes
   // written by their producers (GEMM epilogues, core kernels), never re-split
   bool cp, cp_lo;
+  bool st_tiled;  // gates / ahn / h stash in the tiled layout of the tensor-core flow-core pipeline
   void *cact_hi, *cact_lo, *y_hi, *y_lo, *zf_hi, *zf_lo, *h_hi, *h_lo;
   void *dG_hi, *dG_lo, *dAh_hi, *dAh_lo, *dO_hi, *dO_lo, *dzf_hi, *dzf_lo, *dC_hi, *dC_lo;
   size_t bytes;
@@ -160,12 +161,14 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
   }
   w->gh = b.take<float>(ghmax);
   const size_t cells = K * M;
+  w->st_tiled = w->cp && core::pipe_tc_supported(d, d.K);
+  const size_t cells_t = w->st_tiled ? K * Tp * round_up_sz((size_t)B, 64) : cells;  // tiled stash: whole 64-sequence tiles
   w->st.y = b.take<float>(cells * d.C);
   w->st.zf = b.take<float>(cells * d.C);
-  w->st.h = b.take<float>(cells * d.H);
+  w->st.h = b.take<float>(cells_t * d.H);
   w->st.c = d.G == 4 ? b.take<float>(cells * d.H) : nullptr;
-  w->st.gates = b.take<float>(cells * d.GH);
-  w->st.ahn = d.G == 3 ? b.take<float>(cells * d.H) : nullptr;
+  w->st.gates = b.take<float>(cells_t * d.GH);
+  w->st.ahn = d.G == 3 ? b.take<float>(cells_t * d.H) : nullptr;
   w->st.o = b.take<float>(cells * d.Co);
   w->st.xin = b.take<float>((cells + M) * d.C);
   // backward
@@ -364,6 +367,7 @@ int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params 
   a.scale_out = scale_out;
   a.flags = w.flags; a.flags_bytes = kFlagInts * sizeof(int);
   if (w.cp) { a.py_hi = w.y_hi; a.py_lo = w.y_lo; a.pzf_hi = w.zf_hi; a.pzf_lo = w.zf_lo; a.ph_hi = w.h_hi; a.ph_lo = w.h_lo; }
+  a.stash_tiled = w.st_tiled ? 1 : 0;
   return core::launch_fwd(a, st);
 }
 
@@ -398,6 +402,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
     a.pdO_hi = w.dO_hi; a.pdO_lo = w.dO_lo; a.pdzf_hi = w.dzf_hi; a.pdzf_lo = w.dzf_lo;
     a.g_b_ih = g->b_ih;
   }
+  a.stash_tiled = w.st_tiled ? 1 : 0;
   LFI_TRY(core::launch_bwd(a, st));
 
   // 2. weight gradients of the per-step matrices as batched (over k) reductions over the M rows
