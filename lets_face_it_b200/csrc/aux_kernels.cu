@@ -277,7 +277,89 @@ __global__ void enc_gate_bwd2_kernel(EncStepBwd2 a, int rows_per_block) {
   atomicAdd(a.gb_ih + e, s_r); atomicAdd(a.gb_ih + E + e, s_u); atomicAdd(a.gb_ih + 2 * E + e, s_n);
   atomicAdd(a.gb_hh + e, s_r); atomicAdd(a.gb_hh + E + e, s_u); atomicAdd(a.gb_hh + 2 * E + e, s_nr);
 }
+// Vectorised variant (E % 4 == 0, 256 % (E/4) == 0): thread = 4 consecutive hidden units of one window, 128-bit loads,
+// 64-bit plane stores, grid-stride over the windows so that every SM keeps several independent rows in flight; the
+// bias-gradient sums are reduced over the block's row lanes in shared memory before the atomics.
+__global__ void __launch_bounds__(256) enc_gate_bwd2_v4_kernel(EncStepBwd2 a) {
+  extern __shared__ float red[];  // [4 sums][rows per iteration][E]
+  const int E = a.E, tpr = E >> 2, rpb = 256 / tpr;
+  const int e = 4 * (threadIdx.x % tpr), rl = threadIdx.x / tpr;
+  float s_r[4] = {0.f, 0.f, 0.f, 0.f}, s_u[4] = {0.f, 0.f, 0.f, 0.f}, s_n[4] = {0.f, 0.f, 0.f, 0.f}, s_nr[4] = {0.f, 0.f, 0.f, 0.f};
+  __nv_bfloat16 *dah_hi = (__nv_bfloat16 *)a.dah_hi, *dah_lo = (__nv_bfloat16 *)a.dah_lo;
+  __nv_bfloat16 *dan_hi = (__nv_bfloat16 *)a.dan_hi, *dan_lo = (__nv_bfloat16 *)a.dan_lo;
+  auto put4 = [](__nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t o, const float (&v)[4]) {
+    __align__(8) __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { h4[c] = __float2bfloat16_rn(v[c]); l4[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h4[c])); }
+    *reinterpret_cast<uint2 *>(hi + o) = *reinterpret_cast<const uint2 *>(h4);
+    if (lo) *reinterpret_cast<uint2 *>(lo + o) = *reinterpret_cast<const uint2 *>(l4);
+  };
+  for (int m = blockIdx.x * rpb + rl; m < a.M; m += gridDim.x * rpb) {
+    const size_t idx = (size_t)m * E + e, g3 = (size_t)m * 3 * E + e;
+    float4 d4 = *reinterpret_cast<const float4 *>(a.dh + idx);
+    const float4 r4 = __ldg(reinterpret_cast<const float4 *>(a.gates + g3)), u4 = __ldg(reinterpret_cast<const float4 *>(a.gates + g3 + E)),
+                 n4 = __ldg(reinterpret_cast<const float4 *>(a.gates + g3 + 2 * E)), a4 = __ldg(reinterpret_cast<const float4 *>(a.ahn + idx));
+    const float4 h4 = a.hprev ? __ldg(reinterpret_cast<const float4 *>(a.hprev + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.dh_extra) {
+      const float4 x4 = *reinterpret_cast<const float4 *>(a.dh_extra + (size_t)m * a.dh_extra_ld + e);
+      d4.x += x4.x; d4.y += x4.y; d4.z += x4.z; d4.w += x4.w;
+    }
+    const float dd[4] = {d4.x, d4.y, d4.z, d4.w}, rg[4] = {r4.x, r4.y, r4.z, r4.w}, ug[4] = {u4.x, u4.y, u4.z, u4.w};
+    const float ng[4] = {n4.x, n4.y, n4.z, n4.w}, an[4] = {a4.x, a4.y, a4.z, a4.w}, hp[4] = {h4.x, h4.y, h4.z, h4.w};
+    float dar[4], dau[4], dan[4], danr[4], dhn[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float dn = dd[c] * (1.0f - ug[c]), du = dd[c] * (hp[c] - ng[c]);
+      dan[c] = dn * (1.0f - ng[c] * ng[c]);
+      dau[c] = du * ug[c] * (1.0f - ug[c]);
+      dar[c] = dan[c] * an[c] * rg[c] * (1.0f - rg[c]);
+      danr[c] = dan[c] * rg[c];
+      dhn[c] = dd[c] * ug[c];
+      s_r[c] += dar[c]; s_u[c] += dau[c]; s_n[c] += dan[c]; s_nr[c] += danr[c];
+    }
+    if (a.dah32) {
+      *reinterpret_cast<float4 *>(a.dah32 + g3) = make_float4(dar[0], dar[1], dar[2], dar[3]);
+      *reinterpret_cast<float4 *>(a.dah32 + g3 + E) = make_float4(dau[0], dau[1], dau[2], dau[3]);
+      *reinterpret_cast<float4 *>(a.dah32 + g3 + 2 * E) = make_float4(danr[0], danr[1], danr[2], danr[3]);
+      *reinterpret_cast<float4 *>(a.dan32 + idx) = make_float4(dan[0], dan[1], dan[2], dan[3]);
+    }
+    if (dah_hi) {
+      put4(dah_hi, dah_lo, g3, dar); put4(dah_hi, dah_lo, g3 + E, dau); put4(dah_hi, dah_lo, g3 + 2 * E, danr);
+      put4(dan_hi, dan_lo, idx, dan);
+    }
+    *reinterpret_cast<float4 *>(a.dh + idx) = make_float4(dhn[0], dhn[1], dhn[2], dhn[3]);
+  }
+  // reduce the four sums over the block's row lanes, then one atomic per (unit, sum) and block
+  float *q = red + (size_t)rl * E + e;
+  const size_t plane = (size_t)rpb * E;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { q[c] = s_r[c]; q[plane + c] = s_u[c]; q[2 * plane + c] = s_n[c]; q[3 * plane + c] = s_nr[c]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * E; i += 256) {
+    const int which = i / E, u = i - which * E;
+    float s = 0.f;
+    for (int r = 0; r < rpb; ++r) s += red[(size_t)which * plane + (size_t)r * E + u];
+    if (which == 0) { atomicAdd(a.gb_ih + u, s); atomicAdd(a.gb_hh + u, s); }
+    else if (which == 1) { atomicAdd(a.gb_ih + E + u, s); atomicAdd(a.gb_hh + E + u, s); }
+    else if (which == 2) atomicAdd(a.gb_ih + 2 * E + u, s);
+    else atomicAdd(a.gb_hh + 2 * E + u, s);
+  }
+}
+
 int enc_gate_bwd2(const EncStepBwd2 &a, cudaStream_t st) {
+  auto al16 = [](const void *p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
+  const int tpr = a.E / 4;
+  if (a.E % 4 == 0 && tpr >= 1 && tpr <= 256 && 256 % tpr == 0 && al16(a.dh) && al16(a.gates) && al16(a.ahn) && al16(a.hprev) &&
+      al16(a.dah32) && al16(a.dan32) && al16(a.dh_extra) && (a.dh_extra == nullptr || a.dh_extra_ld % 4 == 0) &&
+      (((uintptr_t)a.dah_hi | (uintptr_t)a.dah_lo | (uintptr_t)a.dan_hi | (uintptr_t)a.dan_lo) & 7) == 0) {
+    const int rpb = 256 / tpr;
+    int blocks = (a.M + rpb - 1) / rpb;
+    if (blocks > 148 * 6) blocks = 148 * 6;
+    const size_t smem = (size_t)4 * rpb * a.E * sizeof(float);
+    enc_gate_bwd2_v4_kernel<<<blocks, 256, smem, st>>>(a);
+    LFI_LAUNCH_CHECK();
+    return LFI_OK;
+  }
   const int threads = a.E >= 256 ? 256 : (a.E >= 128 ? 128 : 64);
   const int cb = (a.E + threads - 1) / threads;
   int rpb = 32;

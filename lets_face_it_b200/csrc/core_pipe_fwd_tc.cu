@@ -530,8 +530,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
 
 // ------------------------------------------------------------------------------------------------
 bool pipe_tc_supported(const Dims &d, int nk) {
-  static const bool on = env_flag("LFI_CORE_TC", true);
-  if (!on || !pipe_supported(d, nk, false)) return false;
+  if (!env_flag("LFI_CORE_TC", true) || !pipe_supported(d, nk, false)) return false;  // read at call time (tests toggle it)
   if (d.Cip % 4 != 0 || d.Ci > 32 || d.Co > 64 || d.H != 2 * PUC) return false;
   return plan_tc(d).total <= 227 * 1024;
 }

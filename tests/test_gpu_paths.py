@@ -71,6 +71,34 @@ def test_pipelined_core_matches_wavefront_kernels(B):
         assert err < 1e-4, (k, err)
 
 
+@pytest.mark.parametrize("B", [256, 100])
+def test_tensor_core_flow_core_matches_ffma_core(B):
+    """Tensor-core modes, final_model.yaml, T=80: the forward flow core with its recurrent / z1 / LinearZeros products as
+    tcgen05.mma on split-bf16 operand planes (tiled gate stash, read by the backward pipeline) against the FFMA pipeline
+    (LFI_CORE_TC=0, row-major stash) in the same GEMM mode: z / NLL within 5e-5 (three-product split-bf16 is fp32-grade),
+    per-tensor gradients within 2e-3 relative L2; and z within the 1e-4 parity gate of the fp32 wavefront kernels.
+    B=100 leaves a ragged second tile whose padding rows live only in the tiled stash."""
+    hp, m = _model("bf16x3")
+    m.train()
+    batch = to_device(kat_batch(hp, B, 80, seed=14), DEV)
+    z1, n1, g1 = _fwd_bwd(m, batch)
+    with _env(LFI_CORE_TC="0"):
+        z0, n0, g0 = _fwd_bwd(m, batch)
+    assert relerr(z1, z0) < 5e-5
+    assert relerr(n1, n0) < 5e-5
+    for k in g0:
+        ref = g0[k].double()
+        err = float((g1[k].double() - ref).norm() / ref.norm().clamp_min(1e-30))
+        assert err < 2e-3, (k, err)
+    from lets_face_it_b200 import _cabi as cabi
+
+    m.gemm_mode = cabi.GEMM_FP32
+    with _env(LFI_CORE_PIPE="0"):
+        z32, n32, _ = _fwd_bwd(m, batch)
+    assert relerr(z1, z32) < 1e-4
+    assert relerr(n1, n32) < 1e-4
+
+
 def test_full_size_roundtrip_and_sharding_in_parity_mode():
     """BASELINE configs[1] size (B=256, T=80) in the bf16x3 mode the bench runs in: forward -> invert reproduces the input
     frames (encode / decode round trip through the pipelined core, the fused GRU epilogue, the operand planes and the
