@@ -293,6 +293,7 @@ def run_ours(a):
         data["p1_face"] = torch.zeros(Bs, START_TS, hy.C, device=dev)
         model.hparams.Infer["eps"] = 0.7
         model.inference(START_TS + min(Tg, 32), data={k: v[:, :START_TS + min(Tg, 32)] for k, v in data.items()})
+        model.inference(START_TS + Tg, data=data)  # full-size warm-up: workspace allocation and first touch stay outside the timed run
         n0 = L.lfi_launch_count()
         ms_s = timed(lambda: model.inference(START_TS + Tg, data=data), 1)
         sample = {"value": Bs * Tg * world / (ms_s * 1e-3), "unit": "frames/s", "sequences_per_gpu": Bs, "frames_per_sequence": Tg, "eps": 0.7,

@@ -849,6 +849,13 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
     const int per = (nkb + sk - 1) / sk;
     sk = (nkb + per - 1) / per;
     p.splitk = sk;
+  } else if (g.epi == LFI_EPI_ACCUM && nkb >= 64 && tiles < 4L * g_sms) {
+    // a partly filled last wave: pick the split whose tile count quantises best (time ~ waves / split)
+    double best = (double)((tiles + g_sms - 1) / g_sms);
+    for (int sk = 2; sk <= 8 && sk <= nkb / 16; ++sk) {
+      const double cost = (double)((tiles * sk + g_sms - 1) / g_sms) / sk * 1.03;  // small charge for the red.add epilogue
+      if (cost < best - 1e-9) { best = cost; p.splitk = sk; }
+    }
   }
   p.C = g.C; p.ldc = g.ldc; p.sC = g.sC; p.bias = g.bias; p.sBias = g.sBias; p.aux = g.aux; p.ldaux = g.ldaux; p.sAux = g.sAux;
   p.epi = g.epi;
