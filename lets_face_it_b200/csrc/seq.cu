@@ -205,6 +205,10 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
                       size_t gws_bytes, cudaStream_t st) {
   const int B = bt->B, T = bt->T;
   const size_t M = (size_t)Tp * B;
+  const bool lo = mode == LFI_GEMM_BF16X3;
+  // ---- phase 1 (caller's stream): window gathers of the "enc: none" modalities, input projections, W_hh planes ----------
+  int mods[LFI_NMOD], nmods = 0;
+  bool all_fused = true;
   for (int m = 0; m < LFI_NMOD; ++m) {
     const int hist = s->hist[m];
     if (hist <= 0) continue;
@@ -221,9 +225,17 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
       LFI_TRY(gemm_dispatch(mode, g, gws, gws_bytes, st));
     }
     EncWs &ew = enc[m];
-    const bool lo = mode == LFI_GEMM_BF16X3;
     if (ew.planes && project)  // W_hh planes: once per call (weights change every optimizer step)
       LFI_TRY(split_to_planes(p->enc_w_hh[m], 3 * E, E, E, 0, 1, ew.whh_hi, lo ? ew.whh_lo : nullptr, st));
+    mods[nmods++] = m;
+    all_fused = all_fused && ew.planes && E % 64 == 0 && env_flag("LFI_FUSED_GRU_FWD", true);
+  }
+  // ---- phase 2: the window recurrences.  With the fused GRU launches (operands in plane form, no shared scratch) the
+  //      modalities are independent chains: they run on parallel streams forked from / joined to the caller's, so that the
+  //      nearly empty last wave of one launch (448 tiles on 148 persistent CTAs) is filled by the other chain's CTAs. --------
+  auto chain = [&](int m, cudaStream_t cs) -> int {
+    const int hist = s->hist[m], E = s->ehid[m];
+    EncWs &ew = enc[m];
     for (int sidx = 0; sidx < hist; ++sidx) {
       float *hprev = nullptr, *hcur;
       const int cur = stash ? sidx : (sidx & 1), prv = stash ? sidx - 1 : ((sidx - 1) & 1);
@@ -236,7 +248,7 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
           gg.pA = plane_ref((uint16_t *)ew.hp_hi + (size_t)prv * M * E, lo ? (uint16_t *)ew.hp_lo + (size_t)prv * M * E : nullptr, E);
           gg.pB = plane_ref(ew.whh_hi, ew.whh_lo, E);
         }
-        LFI_TRY(gemm_dispatch(mode, gg, gws, gws_bytes, st));
+        LFI_TRY(gemm_dispatch(mode, gg, gws, gws_bytes, cs));
       }
       aux::EncStep a;
       a.xp = ew.xp; a.gh = sidx ? gh : nullptr; a.b_ih = p->enc_b_ih[m]; a.b_hh = p->enc_b_hh[m];
@@ -257,13 +269,36 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
         q.E = E; q.s = sidx; q.hist = hist; q.B = B; q.T = T; q.t0 = t0;
         q.xp = a.xp; q.b_ih = a.b_ih; q.b_hh = a.b_hh; q.mask = a.mask; q.hprev = a.hprev;
         q.h = a.h; q.gates = a.gates; q.ahn = a.ahn; q.cond = a.cond; q.cond_ld = a.cond_ld; q.h_hi = a.h_hi; q.h_lo = a.h_lo;
-        LFI_TRY(gemm_dispatch(mode, gg, gws, gws_bytes, st));
+        LFI_TRY(gemm_dispatch(mode, gg, gws, gws_bytes, cs));
         continue;
       }
-      LFI_TRY(aux::enc_gate_fwd(a, st));
+      LFI_TRY(aux::enc_gate_fwd(a, cs));
+    }
+    return LFI_OK;
+  };
+  static cudaStream_t side[LFI_NMOD] = {nullptr, nullptr, nullptr, nullptr};
+  static cudaEvent_t ev_fork = nullptr, ev_join[LFI_NMOD] = {nullptr, nullptr, nullptr, nullptr};
+  const bool par = nmods > 1 && all_fused && env_flag("LFI_ENC_STREAMS", true);
+  if (!par) {
+    for (int i = 0; i < nmods; ++i) LFI_TRY(chain(mods[i], st));
+    return LFI_OK;
+  }
+  if (!ev_fork) {
+    LFI_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < LFI_NMOD; ++i) {
+      LFI_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
+      LFI_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
     }
   }
-  return LFI_OK;
+  LFI_CUDA(cudaEventRecord(ev_fork, st));
+  for (int i = 1; i < nmods; ++i) LFI_CUDA(cudaStreamWaitEvent(side[i], ev_fork, 0));
+  int rc = LFI_OK;
+  for (int i = 0; i < nmods && rc == LFI_OK; ++i) rc = chain(mods[i], i == 0 ? st : side[i]);
+  for (int i = 1; i < nmods; ++i) {  // always join, also on error
+    cudaEventRecord(ev_join[i], side[i]);
+    cudaStreamWaitEvent(st, ev_join[i], 0);
+  }
+  return rc;
 }
 
 // cond_transform for all K steps, then the c-part of the gate-ih product (models.py:187-190, 206-208)
