@@ -440,7 +440,27 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   a.stash_tiled = w.st_tiled ? 1 : 0;
   LFI_TRY(core::launch_bwd(a, st));
 
-  // 2. weight gradients of the per-step matrices as batched (over k) reductions over the M rows
+  // 2. weight gradients of the per-step matrices as batched (over k) reductions over the M rows.  With every operand in
+  //    plane form (no shared scratch) they are independent of the rest of the backward pass: they run on a side stream,
+  //    concurrently with the cond_transform / encoder backward below (small-output long-K launches and a latency-bound
+  //    chain fill each other's idle SMs), and are joined before the call returns.
+  static cudaStream_t wg_stream = nullptr;
+  static cudaEvent_t wg_fork = nullptr, wg_join = nullptr;
+  const bool wg_par = w.cp && env_flag("LFI_WGRAD_STREAM", true);
+  cudaStream_t st_main = st;
+  if (wg_par) {
+    if (!wg_stream) {
+      LFI_CUDA(cudaStreamCreateWithFlags(&wg_stream, cudaStreamNonBlocking));
+      LFI_CUDA(cudaEventCreateWithFlags(&wg_fork, cudaEventDisableTiming));
+      LFI_CUDA(cudaEventCreateWithFlags(&wg_join, cudaEventDisableTiming));
+    }
+    LFI_CUDA(cudaEventRecord(wg_fork, st_main));
+    LFI_CUDA(cudaStreamWaitEvent(wg_stream, wg_fork, 0));
+    st = wg_stream;
+  }
+  auto join_wgrads = [&]() {
+    if (wg_par) { cudaEventRecord(wg_join, wg_stream); cudaStreamWaitEvent(st_main, wg_join, 0); }
+  };
   auto off16 = [](void *base, size_t n) -> void * { return base ? (void *)((uint16_t *)base + n) : nullptr; };
   auto wgrad = [&](int Mo, int No, size_t red, const float *A, int lda, long sA, const float *Bm, int ldb, long sB, float *Cm,
                    int ldc, long sC, PlaneRef pa = PlaneRef{nullptr, nullptr, 0, 0}, PlaneRef pb = PlaneRef{nullptr, nullptr, 0, 0}) -> int {
@@ -462,6 +482,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   LFI_TRY(wgrad(C, C, M, w.st.y, C, (long)(M * C), w.dzf, C, (long)(M * C), g->w, C, (long)C * C,
                 plane_ref(w.y_hi, w.y_lo, C, (long)(M * C)), plane_ref(w.dzf_hi, w.dzf_lo, C, (long)(M * C))));       // dW (1x1 conv)
   if (!w.cp) LFI_TRY(aux::colsum(g->b_ih, w.dG, K * GH, (int)M, K * GH, 1.0f, st));  // (planes: reduced inside the core kernel)
+  st = st_main;
 
   // 3. cond_transform backward
   {
@@ -483,7 +504,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   int enc_lo = -1;
   for (int m = 0; m < LFI_NMOD; ++m)
     if (s->hist[m] > 0 && s->ehid[m] > 0) { enc_lo = d.enc_offe[m]; break; }
-  if (enc_lo < 0) return LFI_OK;
+  if (enc_lo < 0) { join_wgrads(); return LFI_OK; }
   {
     GemmArgs q = gemm_args(0, 0, (int)M, d.Fe - enc_lo, K * D, w.dC, K * D, WcF + enc_lo, d.Fe, w.dcond + enc_lo, d.Fe, 0);
     if (w.cp) q.pA = plane_ref(w.dC_hi, w.dC_lo, K * D);
@@ -559,8 +580,10 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   static cudaEvent_t ev_fork = nullptr, ev_join[LFI_NMOD] = {nullptr, nullptr, nullptr, nullptr};
   const bool par = nmods > 1 && all_planes && env_flag("LFI_ENC_STREAMS", true);
   if (!par) {
-    for (int i = 0; i < nmods; ++i) LFI_TRY(enc_bwd(mods[i], st));
-    return LFI_OK;
+    int rc = LFI_OK;
+    for (int i = 0; i < nmods && rc == LFI_OK; ++i) rc = enc_bwd(mods[i], st);
+    join_wgrads();
+    return rc;
   }
   if (!ev_fork) {
     LFI_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -577,6 +600,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
     cudaEventRecord(ev_join[i], side[i]);
     cudaStreamWaitEvent(st, ev_join[i], 0);
   }
+  join_wgrads();
   return rc;
 }
 
