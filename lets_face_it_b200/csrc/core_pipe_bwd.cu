@@ -9,6 +9,7 @@
 // registers over all frames and flushed with one round of atomics at the end of the launch.
 #include "core_pipe.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
@@ -28,7 +29,8 @@ struct PipePlanB {  // offsets in floats
   int whh, wz, wf, wT, vec, dact, dhc, dzf, dor, dz1, total;
   int pC, pO;
 };
-constexpr int PZ1 = 32;  // row pitch of the dz1 partial-sum buffers (Cip <= 32)
+constexpr int PZ1 = 32;
+__device__ int g_core_timing_b = 0;  // debug: LFI_CORE_TIMING=1 prints the phase cycle counts of one CTA  // row pitch of the dz1 partial-sum buffers (Cip <= 32)
 
 __host__ __device__ inline PipePlanB plan_pipe_bwd(const Dims &d) {
   PipePlanB p;
@@ -99,6 +101,9 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
   int *my_flag = progress + ((size_t)(p * K + k) * 2 + c);
   int it = 0;
   bool x3_pending = false;
+  const bool timing = g_core_timing_b && tid == 0 && c == 0 && p == 0 && (k == 8 || k == 0 || k == K - 1);
+  long long tacc[12] = {0}, tprev = 0;
+#define TSTAMPB(i) do { if (timing) { const long long now_ = clock64(); tacc[i] += now_ - tprev; tprev = now_; } } while (0)
 
   // per-channel gradient accumulators (flushed once at the end)
   float gbhh[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, gbin[2] = {0.f, 0.f};
@@ -114,6 +119,7 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
 
     for (int t = Tp - 1; t >= 0; --t, ++it) {
       const size_t cell = (size_t)k * Tp + t;
+      if (timing) tprev = clock64();
       // ---- 0. prefetch the gate stash of this thread's 8 rows x 2 units ----------------------------------------------
       float2 pg[8][3], pa[8], ph[8];
       {
@@ -150,6 +156,14 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
           }
         }
       }
+      float yv[2][4];  // ActNorm outputs of this thread's 1x1-conv-backward outputs (d logs), requested early
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = 2 * krp + i;
+          yv[i][j] = (kact && r < nmy && 4 * kcq + j < C) ? __ldg(a.st.y + (cell * B + row0 + lr0 + r) * C + 4 * kcq + j) : 0.f;
+        }
       // coupling stash of this CTA's rows (lane = coupling channel, row = warp + 8n): independent of stage k+1, requested
       // before the wait so that the latency hides behind it
       constexpr int NR = PRH / 8;
@@ -179,6 +193,7 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
         }
         __syncthreads();
       }
+      TSTAMPB(0);
       // ---- 2. coupling backward (models.py:331-341) on this CTA's 32 rows ---------------------------------------------
       float c_dz[NR], c_dx1[NR];
 #pragma unroll
@@ -202,7 +217,7 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
           const float dz2n = c_dz[n];
           if (d.affine) {
             const float shift = c_o[n].x, sc = c_o[n].y, z2 = c_z2[n];
-            const float sg = sigmoidf_(sc + 2.0f), s = fmaxf(sg, d.eps);
+            const float sg = fast_sigmoid(sc + 2.0f), s = fmaxf(sg, d.eps);
             const float ds = dz2n * (z2 + shift) + dld / s;
             dz2 = dz2n * s;
             const float dsc = (sg >= d.eps) ? ds * sg * (1.0f - sg) : 0.f;
@@ -230,13 +245,9 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
         dlin[j * PHS + lr0 + r] = v;
         peer[pl.dact + PUC * PHS + j * PHS + lr0 + r] = v;
       }
-      for (int e = tid; e < nmy * Co; e += PNT) {
-        const int r = e / Co, j = e - r * Co;
-        const size_t o = (cell * B + row0 + lr0 + r) * Co + j;
-        if (a.dO) a.dO[o] = dor[r * pO + j];
-        if (a.pdO_hi) put_plane(a.pdO_hi, a.pdO_lo, o, dor[r * pO + j]);
-      }
+      TSTAMPB(1);
       cluster.sync();  // X1: dlin of all 64 rows present in both CTAs
+      TSTAMPB(2);
       if (t < Tp - 1) {
 #pragma unroll
         for (int x = 0; x < 2; ++x) {  // the peer's share of d h[k][t] (it rewrites this buffer only after X2 of this frame)
@@ -260,6 +271,7 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) { dh[r][0] = fmaf(av[r], wv.x, dh[r][0]); dh[r][1] = fmaf(av[r], wv.y, dh[r][1]); }
       }
+      TSTAMPB(3);
       // ---- 4. GRU gate backward ------------------------------------------------------------------------------------------
       float dar[8][2], dau[8][2], dan[8][2], dnr[8][2];
 #pragma unroll
@@ -310,6 +322,7 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
           }
         }
       }
+      TSTAMPB(4);
       // ---- 5. dh_prev partial = dA_h W_hh (own units -> carry, peer units -> peer) ; dz1 partial = dA_i W_ih[:, :Ci] -----
       float ip[8][4], jp[2][4];
 #pragma unroll
@@ -366,7 +379,9 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
         *reinterpret_cast<float4 *>(ob) = make_float4(jp[0][0], jp[0][1], jp[0][2], jp[0][3]);
         *reinterpret_cast<float4 *>(ob + PZ1) = make_float4(jp[1][0], jp[1][1], jp[1][2], jp[1][3]);
       }
+      TSTAMPB(5);
       cluster.sync();  // X2: partial sums exchanged
+      TSTAMPB(6);
 
       // ---- 6. finish d(1x1 conv output), dy = dzf @ W^T, ActNorm backward (modules.py:45-66) ------------------------------
       for (int e = tid; e < PRH * Ci; e += PNT) {
@@ -374,12 +389,6 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
         dzf[r * pC + i] += dz1[r * PZ1 + i] + dz1[PRH * PZ1 + r * PZ1 + i];
       }
       __syncthreads();
-      for (int e = tid; e < nmy * C; e += PNT) {
-        const int r = e / C, j = e - r * C;
-        const size_t o = (cell * B + row0 + lr0 + r) * C + j;
-        if (a.dzf) a.dzf[o] = dzf[r * pC + j];
-        if (a.pdzf_hi) put_plane(a.pdzf_hi, a.pdzf_lo, o, dzf[r * pC + j]);
-      }
       if (kact) {
         float dy[2][4];
 #pragma unroll
@@ -402,7 +411,7 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
               if (4 * kcq + j < C) {
                 const float dxv = dy[i][j] * ans[4 * kcq + j];
                 gab[j] += dxv;
-                gal[j] += dy[i][j] * a.st.y[off + j];
+                gal[j] += dy[i][j] * yv[i][j];
                 if (k > 0) a.dx[off + j] = dxv;
               }
             }
@@ -411,8 +420,22 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
       }
       if (k > 0) {
         __syncthreads();
-        if (tid == 0) { __threadfence(); st_release_gpu_b(my_flag, it + 1); }
+        if (tid == 0) st_release_gpu_b(my_flag, it + 1);  // release at gpu scope, cumulative over the CTA barrier above
       }
+      // stash of the weight-gradient operands (dO, dzf: fp32 and planes): off the stage-to-stage path
+      for (int e = tid; e < nmy * Co; e += PNT) {
+        const int r = e / Co, j = e - r * Co;
+        const size_t o = (cell * B + row0 + lr0 + r) * Co + j;
+        if (a.dO) a.dO[o] = dor[r * pO + j];
+        if (a.pdO_hi) put_plane(a.pdO_hi, a.pdO_lo, o, dor[r * pO + j]);
+      }
+      for (int e = tid; e < nmy * C; e += PNT) {
+        const int r = e / C, j = e - r * C;
+        const size_t o = (cell * B + row0 + lr0 + r) * C + j;
+        if (a.dzf) a.dzf[o] = dzf[r * pC + j];
+        if (a.pdzf_hi) put_plane(a.pdzf_hi, a.pdzf_lo, o, dzf[r * pC + j]);
+      }
+      TSTAMPB(7);
       // 5b. dh_prev partial sums: needed by this stage's next frame only, so they run after the hand-off to stage k-1.
       //     Buffer 1 still holds dau; buffer 0 (dan) is free since X2.
       stage_to(buf0, dar);
@@ -433,10 +456,14 @@ core_bwd_pipe(const BwdArgs a, const int P, const int ntiles, int *progress) {
       // X3 (split): this CTA is done with both staging buffers and has delivered the peer's dh_prev share
       asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
       x3_pending = true;
+      TSTAMPB(8);
     }
     if (x3_pending) { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); x3_pending = false; }
   }
 
+  if (timing)
+    printf("core_bwd_pipe stage %d: frames %d cycles/frame: stash prefetch+wait %lld | coupling bwd+dlin %lld | X1 %lld | dh=dlin Wf %lld | gate bwd+dG/dAh stores %lld | dz1 products %lld | X2 %lld | dzf, 1x1 bwd, publish %lld | dh_prev products %lld\n",
+           k, it, tacc[0] / it, tacc[1] / it, tacc[2] / it, tacc[3] / it, tacc[4] / it, tacc[5] / it, tacc[6] / it, tacc[7] / it, tacc[8] / it);
   // ---- flush the per-channel gradients -------------------------------------------------------------------------------
 #pragma unroll
   for (int g = 0; g < 3; ++g)
@@ -471,6 +498,8 @@ int pipe_bwd_smem_bytes(const Dims &d) { return plan_pipe_bwd(d).total * (int)si
 
 int launch_bwd_pipe(const BwdArgs &a, cudaStream_t st) {
   const int K = a.d.K;
+  static const int timing = getenv("LFI_CORE_TIMING") ? atoi(getenv("LFI_CORE_TIMING")) : 0;
+  if (timing) cudaMemcpyToSymbolAsync(g_core_timing_b, &timing, sizeof(int), 0, cudaMemcpyHostToDevice, st);
   const int bytes = pipe_bwd_smem_bytes(a.d);
   const int ntiles = (a.B + PR - 1) / PR;
   int nsm = 0, dev = 0;
