@@ -82,6 +82,12 @@ typedef struct lfi_batch {
 const char *lfi_last_error(void);
 int lfi_abi_version(void);
 long lfi_launch_count(void); /* kernels launched by this library since load (bench.py gpu_launches) */
+/* Data-parallel hook (the one exchange of the path is the gradient all-reduce after
+ * LetsFaceItGlow.training_step's backward, lets_face_it_glow.py:39-59).  When an event (cudaEvent_t) is set, the next
+ * lfi_seq_train_bwd records it on its stream as soon as the gradients of the flow-step weights (wc, bc, w_ih, b_ih, w_hh,
+ * b_hh, wf, bf, lf) are final, i.e. before the encoder backward: the caller can start reducing that bucket while the
+ * rest of the call runs.  NULL clears the hook. */
+int lfi_set_grad_ready_event(void *event);
 
 /* ---- sizes ------------------------------------------------------------------------------- */
 int lfi_feature_dim(const lfi_shape *s);        /* F  = FeatureEncoder.dim (models.py:96-125)            */

@@ -48,6 +48,7 @@ SYMBOLS = {
     "lfi_last_error": (C.c_char_p, []),
     "lfi_abi_version": (_I, []),
     "lfi_launch_count": (_L, []),
+    "lfi_set_grad_ready_event": (_I, [_P]),
     "lfi_feature_dim": (_I, [_SH]),
     "lfi_feature_dim_folded": (_I, [_SH]),
     "lfi_start_ts": (_I, [_SH]),

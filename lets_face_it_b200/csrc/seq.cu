@@ -345,7 +345,11 @@ static int check_batch(const lfi_shape *s, const Dims &d, const lfi_batch *b, in
 
 using namespace lfi;
 
+static cudaEvent_t g_grad_ready_event = nullptr;
+
 extern "C" {
+
+int lfi_set_grad_ready_event(void *event) { g_grad_ready_event = (cudaEvent_t)event; return LFI_OK; }
 
 int lfi_feature_dim(const lfi_shape *s) { Dims d; return make_dims(s, &d) == LFI_OK ? d.F : -1; }
 int lfi_feature_dim_folded(const lfi_shape *s) { Dims d; return make_dims(s, &d) == LFI_OK ? d.Fe : -1; }
@@ -499,6 +503,17 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
     if (w.cp) r.pA = plane_ref(w.dC_hi, w.dC_lo, K * D);
     LFI_TRY(gemm_dispatch(gemm_mode, r, gws, gws_bytes, st));
     LFI_TRY(aux::unfold_wc_grad(g->wc, w.dWcF, d, *s, st));
+  }
+  if (g_grad_ready_event) {  // data parallel: every flow-step weight gradient is final here, once the side-stream GEMMs are too
+    if (wg_par) {  // record on the side stream, ordered after this point of the main stream (no early join of the main stream)
+      static cudaEvent_t ev_unfold = nullptr;
+      if (!ev_unfold) LFI_CUDA(cudaEventCreateWithFlags(&ev_unfold, cudaEventDisableTiming));
+      LFI_CUDA(cudaEventRecord(ev_unfold, st));
+      LFI_CUDA(cudaStreamWaitEvent(wg_stream, ev_unfold, 0));
+      LFI_CUDA(cudaEventRecord(g_grad_ready_event, wg_stream));
+    } else {
+      LFI_CUDA(cudaEventRecord(g_grad_ready_event, st));
+    }
   }
   // d cond for the encoder columns only (inputs carry no gradient)
   int enc_lo = -1;

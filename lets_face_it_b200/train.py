@@ -41,6 +41,13 @@ class Trainer:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         self._dnll = {}
+        # data parallel: the flow-step bucket of the gradient is reduced on a side stream while the encoder backward runs
+        self.overlap = self.world > 1 and dev.type == "cuda"
+        if self.overlap:
+            self._side = torch.cuda.Stream(device=dev)
+            self._ev = torch.cuda.Event()
+            self._ev.record()  # creates the underlying cudaEvent
+            self._bucket = flow_grad_range(self.eng.blocks)
 
     def broadcast_parameters(self, src=0):
         """Replicas start identical (and share the ActNorm data-dependent init of rank `src`)."""
@@ -62,9 +69,25 @@ class Trainer:
         if key not in self._dnll:
             self._dnll[key] = torch.full((Tp, B), 1.0 / (Tp * B), device=eng.theta.device)
         self.gflat.zero_()
-        eng.train_backward(z, self._dnll[key], self.gflat)
         g = self.gflat[:eng.n_theta]
-        allreduce_flat_gradient(g, self.world, self.pg)  # sum; averaged by grad_scale below
+        if self.overlap:
+            L = cabi.lib()
+            L.lfi_set_grad_ready_event(self._ev.cuda_event)
+            try:
+                eng.train_backward(z, self._dnll[key], self.gflat)
+            finally:
+                L.lfi_set_grad_ready_event(None)
+            lo, hi = self._bucket
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._ev)  # recorded inside the backward call, before the encoder backward
+                work = torch.distributed.all_reduce(g[lo:hi], op=torch.distributed.ReduceOp.SUM, group=self.pg, async_op=True)
+            for a0, a1 in ((0, lo), (hi, eng.n_theta)):  # ActNorm / 1x1-conv and encoder gradients: final only now
+                if a1 > a0:
+                    torch.distributed.all_reduce(g[a0:a1], op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            work.wait()
+        else:
+            eng.train_backward(z, self._dnll[key], self.gflat)
+            allreduce_flat_gradient(g, self.world, self.pg)  # sum; averaged by grad_scale below
         self.step_count += 1
         cabi.check(cabi.lib().lfi_clip_adam(eng.theta.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), eng.n_theta,
                                             self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0 / self.world,
@@ -83,6 +106,23 @@ def allreduce_flat_gradient(g, world, group=None):
     if world > 1:
         torch.distributed.all_reduce(g, op=torch.distributed.ReduceOp.SUM, group=group)
     return g
+
+
+# flat-buffer blocks whose gradients are final before the encoder backward (engine.py: _STEP_BLOCKS_F, contiguous)
+_FLOW_BUCKET = ("wc", "bc", "w_ih", "b_ih", "w_hh", "b_hh", "wf", "bf", "lf")
+
+
+def flow_grad_range(blocks):
+    """[lo, hi) of the flat gradient covered by the flow-step weight blocks (`blocks`: name -> (offset, numel per step,
+    steps), Engine.blocks).  The blocks must be adjacent in the flat layout (only alignment padding between them)."""
+    spans = sorted((blocks[n][0], blocks[n][0] + blocks[n][1] * blocks[n][2]) for n in _FLOW_BUCKET if n in blocks)
+    if not spans:
+        return 0, 0
+    lo, hi = spans[0][0], spans[-1][1]
+    inside = {n for n, (o, m, k) in blocks.items() if lo <= o < hi}
+    if inside != {n for n in _FLOW_BUCKET if n in blocks}:
+        raise RuntimeError("flat layout changed: blocks %s lie inside the flow-step bucket" % sorted(inside - set(_FLOW_BUCKET)))
+    return lo, hi
 
 
 def shard_batch(batch, rank, world):

@@ -69,6 +69,27 @@ def test_shard_batch_rejects_ragged_split():
     assert s["p1_face"].shape[0] == 2 and float(s["p1_face"][0, 0, 0]) == 4.0
 
 
+def test_flow_grad_bucket_is_one_contiguous_range():
+    """The bucket reduced while the encoder backward still runs (train.py: flow_grad_range) must cover exactly the
+    flow-step weight blocks of the flat layout and nothing whose gradient is finished later (ActNorm / 1x1 conv / encoders)."""
+    from lets_face_it_b200.train import flow_grad_range
+
+    blocks, off = {}, 0
+    for name, n, k in [("an_bias", 56, 16), ("an_logs", 56, 16), ("inv_l", 3136, 16), ("inv_u", 3136, 16), ("inv_log_s", 56, 16),
+                       ("wc", 512 * 1560, 16), ("bc", 512, 16), ("w_ih", 384 * 540, 16), ("b_ih", 384, 16), ("w_hh", 384 * 128, 16),
+                       ("b_hh", 384, 16), ("wf", 56 * 128, 16), ("bf", 56, 16), ("lf", 56, 16), ("enc_w_ih.1", 768 * 56, 1),
+                       ("enc_w_hh.1", 768 * 256, 1)]:
+        blocks[name] = (off, n, k)
+        off = (off + n * k + 63) // 64 * 64
+    lo, hi = flow_grad_range(blocks)
+    assert lo == blocks["wc"][0] and hi == blocks["lf"][0] + 56 * 16
+    assert blocks["inv_log_s"][0] + 56 * 16 <= lo and hi <= blocks["enc_w_ih.1"][0]
+    bad = dict(blocks)
+    bad["enc_w_ih.1"] = (blocks["bc"][0] + 1, 8, 1)
+    with pytest.raises(RuntimeError):
+        flow_grad_range(bad)
+
+
 def test_reference_arm_prints_once_under_two_ranks():
     port = 31500 + (os.getpid() % 2000)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
