@@ -170,6 +170,14 @@ int lfi_matmul(const float *a, const float *b, const float *bias, float *c, int 
  * nll[b] = -(logdet[b] + sum_c -0.5 (z^2 + ln 2pi)) / ln 2 */
 int lfi_nll(const float *z, const float *logdet, float *nll, int B, int C, void *stream);
 
+/* Output side of sampling: de-standardise the generated frames and scatter the C = exp + jaw +
+ * neck channels into the 106-wide FLAME vector the render server consumes - generate_motion_from_model.py:39-51 (expand_face_dim)
+ * and :68 (predicted_seq * face_stds + face_means).  x [rows, C] -> out [rows, 106]: out[:, 0:exp] = expression,
+ * out[:, 100:100+jaw] = jaw, out[:, 103:103+neck] = neck, every other column 0.  means / stds [C] or NULL (no
+ * de-standardisation, the bare expand_face_dim).  The product and the sum are rounded separately, as torch does. */
+int lfi_expand_faces(const float *x, const float *means, const float *stds, size_t rows, int exp_dim, int jaw_dim, int neck_dim,
+                     float *out, void *stream);
+
 /* fused gradient-norm clip + Adam over the flat parameter buffer (lets_face_it_glow.py:61-72,
  * final_model.yaml:126,130): two launches, no host sync.  norm_scratch: 2 floats. */
 int lfi_clip_adam(float *theta, float *grad, float *m, float *v, size_t n, float lr, float beta1, float beta2,

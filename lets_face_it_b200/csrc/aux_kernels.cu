@@ -498,5 +498,34 @@ int fill(float *p, float v, size_t n, cudaStream_t st) {
   return LFI_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// generated frames -> 106-wide FLAME vectors (generate_motion_from_model.py:39-51, 68); thread = output element, coalesced
+__global__ void expand_faces_kernel(const float *__restrict__ x, const float *__restrict__ means, const float *__restrict__ stds, size_t rows,
+                                    int exp_dim, int jaw_dim, int neck_dim, float *__restrict__ out) {
+  const int C = exp_dim + jaw_dim + neck_dim;
+  const size_t total = rows * 106;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / 106;
+    const int j = (int)(e - r * 106);
+    int c = -1;
+    if (j < exp_dim) c = j;
+    else if (j >= 100 && j < 100 + jaw_dim) c = exp_dim + (j - 100);
+    else if (j >= 103 && j < 103 + neck_dim) c = exp_dim + jaw_dim + (j - 103);
+    float v = 0.f;
+    if (c >= 0) {
+      v = x[r * C + c];
+      if (means) v = __fadd_rn(__fmul_rn(v, stds[c]), means[c]);  // torch: two rounded operations, no contraction
+    }
+    out[e] = v;
+  }
+}
+int expand_faces(const float *x, const float *means, const float *stds, size_t rows, int exp_dim, int jaw_dim, int neck_dim, float *out,
+                 cudaStream_t st) {
+  if (rows == 0) return LFI_OK;
+  expand_faces_kernel<<<blocks_for(rows * 106), TB, 0, st>>>(x, means, stds, rows, exp_dim, jaw_dim, neck_dim, out);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
 }  // namespace aux
 }  // namespace lfi

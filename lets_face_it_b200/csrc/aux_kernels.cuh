@@ -81,5 +81,7 @@ int clip_adam(float *theta, const float *grad, float *m, float *v, size_t n, flo
 
 int fill(float *p, float v, size_t n, cudaStream_t st);
 
+int expand_faces(const float *x, const float *means, const float *stds, size_t rows, int exp_dim, int jaw_dim, int neck_dim, float *out,
+                 cudaStream_t st);
 }  // namespace aux
 }  // namespace lfi

@@ -932,6 +932,14 @@ int lfi_nll(const float *z, const float *logdet, float *nll, int B, int C, void 
   return aux::nll(z, logdet, nll, B, C, (cudaStream_t)stream);
 }
 
+int lfi_expand_faces(const float *x, const float *means, const float *stds, size_t rows, int exp_dim, int jaw_dim, int neck_dim,
+                     float *out, void *stream) {
+  LFI_REQUIRE(x && out && (means != nullptr) == (stds != nullptr), LFI_ERR_ARG, "lfi_expand_faces: bad argument");
+  LFI_REQUIRE(exp_dim >= 0 && jaw_dim >= 0 && neck_dim >= 0 && exp_dim <= 100 && jaw_dim <= 3 && neck_dim <= 3 && exp_dim + jaw_dim + neck_dim >= 1,
+              LFI_ERR_SHAPE, "lfi_expand_faces: expression/jaw/neck = %d/%d/%d do not fit the 106-wide FLAME vector", exp_dim, jaw_dim, neck_dim);
+  return aux::expand_faces(x, means, stds, rows, exp_dim, jaw_dim, neck_dim, out, (cudaStream_t)stream);
+}
+
 int lfi_clip_adam(float *theta, float *grad, float *m, float *v, size_t n, float lr, float beta1, float beta2, float eps,
                   float max_norm, float grad_scale, int step, float *norm_scratch, void *stream) {
   LFI_REQUIRE(theta && grad && m && v && norm_scratch && step >= 1, LFI_ERR_ARG, "lfi_clip_adam: bad argument");

@@ -41,6 +41,12 @@ class Trainer:
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
         self._dnll = {}
+        # LetsFaceItGlow.__init__ (lets_face_it_glow.py:28-36): state of the mismatched-NLL probe
+        self.last_missmatched_nll = float("inf")
+        self.missmatched_modalities, self.missmatched_nll_name = None, None
+        if getattr(hp, "Train", None) and hp.Train.get("use_negative_nll_loss"):
+            from .glow.utils import get_mismatched_modalities
+            self.missmatched_modalities, self.missmatched_nll_name = get_mismatched_modalities(hp)
         # data parallel: the flow-step bucket of the gradient is reduced on a side stream while the encoder backward runs
         self.overlap = self.world > 1 and dev.type == "cuda"
         if self.overlap:
@@ -54,8 +60,27 @@ class Trainer:
         if self.world > 1:
             torch.distributed.broadcast(self.eng.theta, src, group=self.pg)
 
-    def step(self, batch, masks=None):
-        """One optimizer step on this rank's shard of sequences.  Returns the (device) loss of the shard."""
+    def training_step(self, batch, masks=None):
+        """`LetsFaceItGlow.training_step` (lets_face_it_glow.py:39-55) on the fused step: with `use_negative_nll_loss`, once
+        the last mismatched NLL is positive, one step in ten (python `random`, as the reference) trains on a batch whose
+        interlocutor modalities are shuffled across sequences (`derange_batch`) with the loss scaled by -0.1.  The `and`
+        chain is evaluated in the reference's order, so `random.random()` is consumed on the same steps; the only host
+        synchronisation is the read-back of the probe's NLL on those (10 %) steps.  Returns (loss, deranged)."""
+        import random
+
+        from .glow.utils import derange_batch
+
+        hp = self.model.hparams
+        if (hp.Train["use_negative_nll_loss"] and self.last_missmatched_nll > 0 and random.random() < 0.1
+                and self.missmatched_modalities):
+            loss = self.step(derange_batch(batch, self.missmatched_modalities), masks, loss_scale=-0.1)
+            self.last_missmatched_nll = -float(loss)  # "Loss/missmatched_nll" (:51-52)
+            return loss * -0.1, True
+        return self.step(batch, masks), False
+
+    def step(self, batch, masks=None, loss_scale=1.0):
+        """One optimizer step on this rank's shard of sequences.  Returns the (device) loss of the shard (unscaled);
+        `loss_scale` multiplies the loss the gradient is taken of (the -0.1 of the mismatched-NLL probe)."""
         eng, model = self.eng, self.model
         x0 = batch["p1_face"]
         B, T = x0.shape[0], x0.shape[1]
@@ -65,9 +90,9 @@ class Trainer:
         if model.training and not all(l.actnorm.inited for l in model.glow.flow.layers):
             model._ddi(eng, batch, masks)
         z, nll = eng.train_forward(batch, masks)
-        key = (Tp, B)
+        key = (Tp, B, float(loss_scale))
         if key not in self._dnll:
-            self._dnll[key] = torch.full((Tp, B), 1.0 / (Tp * B), device=eng.theta.device)
+            self._dnll[key] = torch.full((Tp, B), float(loss_scale) / (Tp * B), device=eng.theta.device)
         self.gflat.zero_()
         g = self.gflat[:eng.n_theta]
         if self.overlap:

@@ -386,3 +386,30 @@ def make_masks(hy: Hyper, B, Tp, seed=3):
         else:
             out[m] = None
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Output side of sampling and training-step glue; test infrastructure only.
+def expand_face_dim(seq, exp_dim, jaw_dim, neck_dim):
+    """generate_motion_from_model.py:39-51: [B, T, C] -> [B, T, 106]; expression at 0, jaw at 100, neck at 103."""
+    out = torch.zeros((seq.size(0), seq.size(1), 106))
+    out[:, :, :exp_dim] = seq[:, :, :exp_dim]
+    out[:, :, 100:100 + jaw_dim] = seq[:, :, exp_dim:exp_dim + jaw_dim]
+    out[:, :, 103:103 + neck_dim] = seq[:, :, exp_dim + jaw_dim:exp_dim + jaw_dim + neck_dim]
+    return out
+
+
+def destandardize_expand(seq, means, stds, exp_dim, jaw_dim, neck_dim):
+    """generate_motion_from_model.py:68 then :39-51."""
+    return expand_face_dim(seq * stds + means, exp_dim, jaw_dim, neck_dim)
+
+
+def derange_batch(batch, modalities, permutation):
+    """glow/utils.py:85-100 with the permutation drawn by the caller (shuffle_time=False, the only use in the reference)."""
+    out = {}
+    for m in ("p1_face", "p2_face", "p1_speech", "p2_speech"):
+        if m in modalities:
+            out[m] = batch[m][permutation]
+        elif batch.get(m) is not None:
+            out[m] = batch[m]
+    return out
