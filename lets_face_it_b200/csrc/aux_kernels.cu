@@ -499,6 +499,61 @@ int fill(float *p, float v, size_t n, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// column sums of split-bf16 planes (bias gradients of the flow-step RNN from the dG / dA_h operand planes):
+// block = 16 column groups (4 bf16 each) x 16 row lanes, grid = (column blocks, row splits, batch); one atomic per column and block
+__global__ void colsum_planes_kernel(float *out1, float *out2, int period, int lim2, long so, const __nv_bfloat16 *__restrict__ hi,
+                                     const __nv_bfloat16 *__restrict__ lo, int ld, long sb, int rows, int col0, int cols, int rows_per_block) {
+  __shared__ float part[16][65];
+  const int cg = threadIdx.x & 15, rl = threadIdx.x >> 4;
+  const int j0 = blockIdx.x * 64 + 4 * cg;
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  if (j0 < cols) {
+    const __nv_bfloat16 *ph = hi + (size_t)b * sb + col0 + j0, *pl = lo ? lo + (size_t)b * sb + col0 + j0 : nullptr;
+    for (int r = r0 + rl; r < r1; r += 16) {
+      const uint2 h = *reinterpret_cast<const uint2 *>(ph + (size_t)r * ld);
+      s[0] += __uint_as_float(h.x << 16); s[1] += __uint_as_float(h.x & 0xffff0000u);
+      s[2] += __uint_as_float(h.y << 16); s[3] += __uint_as_float(h.y & 0xffff0000u);
+      if (pl) {
+        const uint2 l = *reinterpret_cast<const uint2 *>(pl + (size_t)r * ld);
+        s[0] += __uint_as_float(l.x << 16); s[1] += __uint_as_float(l.x & 0xffff0000u);
+        s[2] += __uint_as_float(l.y << 16); s[3] += __uint_as_float(l.y & 0xffff0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) part[rl][4 * cg + e] = s[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int j = blockIdx.x * 64 + threadIdx.x;
+    if (j < cols) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) t += part[i][threadIdx.x];
+      atomicAdd(out1 + (size_t)b * so + j, t);
+      if (out2 && (j % period) < lim2) atomicAdd(out2 + (size_t)b * so + j, t);
+    }
+  }
+}
+int colsum_planes(float *out1, float *out2, int period, int lim2, long so, const void *hi, const void *lo, int ld, long sb, int batch, int rows,
+                  int col0, int cols, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0 || batch <= 0) return LFI_OK;
+  LFI_REQUIRE(cols % 4 == 0 && col0 % 4 == 0 && ld % 4 == 0 && sb % 4 == 0 && (((uintptr_t)hi | (uintptr_t)lo) & 7) == 0, LFI_ERR_ARG,
+              "colsum_planes: planes must allow 8-byte accesses");
+  const int cb = (cols + 63) / 64;
+  int rb = (148 * 8 + cb * batch - 1) / (cb * batch);
+  const int maxrb = (rows + 63) / 64;
+  if (rb > maxrb) rb = maxrb;
+  if (rb < 1) rb = 1;
+  const int rpb = (rows + rb - 1) / rb;
+  colsum_planes_kernel<<<dim3(cb, rb, batch), 256, 0, st>>>(out1, out2, period > 0 ? period : 1, lim2, so, (const __nv_bfloat16 *)hi,
+                                                            (const __nv_bfloat16 *)lo, ld, sb, rows, col0, cols, rpb);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // generated frames -> 106-wide FLAME vectors (generate_motion_from_model.py:39-51, 68); thread = output element, coalesced
 __global__ void expand_faces_kernel(const float *__restrict__ x, const float *__restrict__ means, const float *__restrict__ stds, size_t rows,
                                     int exp_dim, int jaw_dim, int neck_dim, float *__restrict__ out) {

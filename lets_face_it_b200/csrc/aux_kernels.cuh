@@ -81,6 +81,9 @@ int clip_adam(float *theta, const float *grad, float *m, float *v, size_t n, flo
 
 int fill(float *p, float v, size_t n, cudaStream_t st);
 
+// out1[b*so + j] (+ out2[..] where (j % period) < lim2) += sum over rows of (hi + lo)[b][r][col0 + j]: column sums of split-bf16 planes
+int colsum_planes(float *out1, float *out2, int period, int lim2, long so, const void *hi, const void *lo, int ld, long sb, int batch, int rows,
+                  int col0, int cols, cudaStream_t st);
 int expand_faces(const float *x, const float *means, const float *stds, size_t rows, int exp_dim, int jaw_dim, int neck_dim, float *out,
                  cudaStream_t st);
 }  // namespace aux

@@ -223,7 +223,10 @@ template <int RPT> static int launch_bwd_t(const BwdArgs &a, cudaStream_t st) {
 }
 
 int launch_bwd(const BwdArgs &a, cudaStream_t st) {
-  if (a.flags && pipe_supported(a.d, a.d.K, true)) return launch_bwd_pipe(a, st);
+  if (a.flags && pipe_supported(a.d, a.d.K, true)) {
+    if (a.stash_tiled && a.pdG_hi && pipe_bwd_tc_supported(a.d)) return launch_bwd_pipe_tc(a, st);  // tensor-core GEMM modes
+    return launch_bwd_pipe(a, st);
+  }
   const int rpt = choose_rpt(a.d, a.B, true, false);
   switch (rpt) {
     case 8: return launch_bwd_t<8>(a, st);

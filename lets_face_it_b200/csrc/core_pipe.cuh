@@ -80,6 +80,8 @@ int launch_bwd_pipe(const BwdArgs &a, cudaStream_t st);
 // tensor-core variants (core_pipe_fwd_tc.cu): gate products as tcgen05.mma on split-bf16 operands, tensor-core GEMM modes only
 bool pipe_tc_supported(const Dims &d, int nk);
 int launch_fwd_pipe_tc(const FwdArgs &a, cudaStream_t st);
+bool pipe_bwd_tc_supported(const Dims &d);
+int launch_bwd_pipe_tc(const BwdArgs &a, cudaStream_t st);
 
 }  // namespace core
 }  // namespace lfi

@@ -485,7 +485,13 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
                 plane_ref(w.dO_hi, w.dO_lo, Co, (long)(M * Co)), ph));                                                 // dWf
   LFI_TRY(wgrad(C, C, M, w.st.y, C, (long)(M * C), w.dzf, C, (long)(M * C), g->w, C, (long)C * C,
                 plane_ref(w.y_hi, w.y_lo, C, (long)(M * C)), plane_ref(w.dzf_hi, w.dzf_lo, C, (long)(M * C))));       // dW (1x1 conv)
-  if (!w.cp) LFI_TRY(aux::colsum(g->b_ih, w.dG, K * GH, (int)M, K * GH, 1.0f, st));  // (planes: reduced inside the core kernel)
+  if (!w.cp) LFI_TRY(aux::colsum(g->b_ih, w.dG, K * GH, (int)M, K * GH, 1.0f, st));  // (planes: reduced inside the core kernel ...
+  if (w.st_tiled && core::pipe_bwd_tc_supported(d)) {
+    // ... except with the tensor-core backward pipeline, which leaves the RNN bias gradients to column sums of its planes:
+    // d b_ih = colsum(dG) (r, u parts also are d b_hh's), d b_hh n part = colsum of the n columns of dA_h)
+    LFI_TRY(aux::colsum_planes(g->b_ih, g->b_hh, GH, 2 * H, 0, w.dG_hi, w.cp_lo ? w.dG_lo : nullptr, K * GH, 0, 1, (int)M, 0, K * GH, st));
+    LFI_TRY(aux::colsum_planes(g->b_hh + 2 * H, nullptr, 1, 0, GH, w.dAh_hi, w.cp_lo ? w.dAh_lo : nullptr, GH, (long)(M * GH), K, (int)M, 2 * H, H, st));
+  }
   st = st_main;
 
   // 3. cond_transform backward
