@@ -42,6 +42,7 @@ struct FwdArgs {
   // 1: st_gates / st_ahn / st_h use the tiled layout of the tensor-core pipeline (core_pipe.cuh: stash_tiled_off), which makes
   // the thread-per-sequence stores of that kernel contiguous; the backward pipeline reads the same layout
   int stash_tiled;
+  int g_tiled;  // 1: G is row-interleaved (core_pipe.cuh: g_tiled_off with ld = g_ld), tensor-core pipeline only
 };
 
 struct InvArgs {

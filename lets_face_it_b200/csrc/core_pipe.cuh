@@ -73,6 +73,9 @@ __host__ __device__ inline size_t stash_tiled_off(size_t cell, int ntiles, int t
   return (((((cell * ntiles + tile) * 2 + c) * 4 + hs) * narr + arr) * 4 + i) * 256;
 }
 
+// Row-interleaved gate-ih pre-activations G (written by the gate-ih GEMM epilogue, GemmArgs::c_tiled32): element (m, n)
+__host__ __device__ inline size_t g_tiled_off(size_t m, size_t n, size_t ld) { return ((m >> 5) * (ld >> 2) + (n >> 2)) * 128 + (m & 31) * 4 + (n & 3); }
+
 bool pipe_supported(const Dims &d, int nk, bool bwd);
 int pipe_bwd_smem_bytes(const Dims &d);
 int launch_fwd_pipe(const FwdArgs &a, cudaStream_t st);

@@ -511,7 +511,7 @@ core_bwd_pipe_tc(const BwdArgs a, const int P, const int ntiles, int *progress) 
 #pragma unroll
         for (int i = 0; i < 2; ++i) dy[i][0] = dy[i][1] = dy[i][2] = dy[i][3] = 0.f;
         const float *x0p = dzf + (2 * krp) * pC, *x1p = x0p + pC;
-#pragma unroll 4
+#pragma unroll 8
         for (int kk = 0; kk < C; ++kk) {
           const float a0 = x0p[kk], a1 = x1p[kk];
           const float4 wv = *reinterpret_cast<const float4 *>(wT + kk * Cp + 4 * kcq);

@@ -259,7 +259,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
 #pragma unroll
             for (int j = 0; j < 4; ++j) z[i][j] = 0.f;
           const float *x0p = xs + (2 * rp) * pC, *x1p = x0p + pC;
-#pragma unroll 4
+#pragma unroll 8
           for (int kk = 0; kk < C; ++kk) {
             const float a0 = x0p[kk], a1 = x1p[kk];
             const float4 wv = *reinterpret_cast<const float4 *>(wsm + kk * Cp + 4 * cq);
@@ -288,19 +288,10 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
         *reinterpret_cast<uint4 *>(peerb + off) = hi;
         *reinterpret_cast<uint4 *>(peerb + off + kAZPlane) = lo;
       }
-      //         gate-ih pre-activations of the first pass (latency hidden behind the cluster barrier and the z1 product)
-      const float *Gb = a.G + ((size_t)t * B + row0 + row) * a.g_ld + (size_t)(k - a.g_k0) * GH + PUC * c + ub;
-      const bool rowok = row < nrows;
-      float4 gq[3][4];
-#pragma unroll
-      for (int g = 0; g < 3; ++g)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) gq[g][i] = rowok ? __ldg(reinterpret_cast<const float4 *>(Gb + g * H + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
       fence_async_smem();
       if (tid == TT) mbar_wait(bar_hh, ph);  // this CTA's recurrent product has consumed h_{t-1}: the peer may overwrite its half
       cluster.sync();  // A: z1 complete in both CTAs
       TSTAMP(3);
-
       // ---- 3. z1 part of the gate-ih product, then the GRU gate math straight from TMEM -------------------------------
       if (tid == TT) {
         fence_after();
@@ -324,6 +315,16 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
         }
         umma_commit(bar_d);
       }
+      //         gate-ih pre-activations of the first pass (requested here: their issue overlaps the z1 product)
+      const size_t gm = (size_t)t * B + row0 + row, gn = (size_t)(k - a.g_k0) * GH + PUC * c + ub;
+      const float *Gb = a.g_tiled ? a.G + g_tiled_off(gm, gn, (size_t)a.g_ld) : a.G + gm * a.g_ld + gn;
+      const size_t gstep_g = a.g_tiled ? (size_t)(H >> 2) * 128 : (size_t)H, gstep_i = a.g_tiled ? 128 : 4;  // next gate / next 4 columns
+      const bool rowok = row < nrows;
+      float4 gq[3][4];
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gq[g][i] = rowok ? __ldg(reinterpret_cast<const float4 *>(Gb + g * gstep_g + i * gstep_i)) : make_float4(0.f, 0.f, 0.f, 0.f);
       for (int e = tid; e < nmy * C; e += PNT) {  // zf stash of this CTA's rows (fp32 and operand planes) while the product runs
         const int r = e / C, j = e - r * C;
         const size_t o = (cell * B + row0 + lr0 + r) * C + j;

@@ -55,6 +55,7 @@ struct Params {
   int vec;  // all fp32 pointers / pitches allow 128-bit accesses
   const __nv_bfloat16 *auxp; int ldauxp; long sAuxp;  // LeakyReLU' mask from the sign of a bf16 plane
   float *colsum; long sColsum;                          // += column sums of the final values
+  int c_tiled;  // row-interleaved C (GemmArgs::c_tiled32)
   int fuse;     // LFI_FUSE_*
   int dbg;
   int cond_vec; // fused GRU forward: the cond slice allows 128-bit stores
@@ -628,7 +629,7 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
                 cs[e] += y;
               }
               if (want_c) {
-                float *dst = C + (size_t)m * p.ldc + n;
+                float *dst = C + (p.c_tiled ? ((size_t)(m >> 5) * (p.ldc >> 2) + (n >> 2)) * 128 + (m & 31) * 4 + (n & 3) : (size_t)m * p.ldc + n);
                 if (p.splitk > 1) {
 #pragma unroll
                   for (int e = 0; e < 4; ++e) atomicAdd(dst + e, x[e]);
@@ -682,7 +683,7 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
               if (auxp) y *= (__bfloat162float(auxp[(size_t)m * p.ldauxp + n]) > 0.f ? 1.f : kLeaky);
               if (colsum) atomicAdd(colsum + n, y);
               if (want_c) {
-                float *dst = C + (size_t)m * p.ldc + n;
+                float *dst = C + (p.c_tiled ? ((size_t)(m >> 5) * (p.ldc >> 2) + (n >> 2)) * 128 + (m & 31) * 4 + (n & 3) : (size_t)m * p.ldc + n);
                 if (p.splitk > 1) atomicAdd(dst, y);
                 else if (p.epi & LFI_EPI_ACCUM) *dst += y;
                 else *dst = y;
@@ -868,6 +869,9 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   if ((g.epi & LFI_EPI_LRELU_BWD) && !g.auxp) p.vec = p.vec && al16(g.aux) && g.ldaux % 4 == 0 && g.sAux % 4 == 0;
   if ((g.epi & LFI_EPI_LRELU_BWD) && g.auxp) p.vec = p.vec && (((uintptr_t)g.auxp & 7) == 0) && g.ldauxp % 4 == 0 && g.sAuxp % 4 == 0;
   if (g.colsum) p.vec = p.vec && g.sColsum % 4 == 0;
+  p.c_tiled = g.c_tiled32;
+  LFI_REQUIRE(!g.c_tiled32 || (!(g.epi & (LFI_EPI_ACCUM | LFI_EPI_ACCUM_PRE)) && g.ldc % 4 == 0 && g.N % 4 == 0), LFI_ERR_ARG,
+              "gemm: row-interleaved output needs a plain store epilogue and 4-column groups");
   if (g.pOut.hi) p.vec = p.vec && al16(g.pOut.hi) && (!g.pOut.lo || al16(g.pOut.lo)) && g.pOut.ld % 4 == 0 && g.pOut.stride % 4 == 0;
 
   CUtensorMap mA0, mA1, mB0, mB1;

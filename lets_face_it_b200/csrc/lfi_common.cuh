@@ -166,6 +166,10 @@ struct GemmArgs {
   // of the final values accumulated into colsum[n] (bias gradients without a second pass over the output)
   const void *auxp; int ldauxp; long sAuxp;
   float *colsum; long sColsum;
+  // tensor-core modes only: C is written row-interleaved, element (m, n) at ((m/32) * (ldc/4) + n/4) * 128 + (m%32) * 4 + n%4
+  // (+ the batch offset sC): 32 consecutive rows of one 4-column group are contiguous, which is what the thread-per-sequence
+  // flow-core kernel reads (core_pipe.cuh: g_tiled_off).  No accumulate epilogues.
+  int c_tiled32;
 };
 int gemm_simt(const GemmArgs &g, cudaStream_t st);
 int gemm_dispatch(int mode, const GemmArgs &g, void *ws, size_t ws_bytes, cudaStream_t st);

@@ -127,7 +127,7 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
   w->cond = b.take<float>(M * d.Fe);
   // operand-plane mode: the cond_transform activations and their gradients exist as bf16 planes only
   w->Cact = w->cp ? nullptr : b.take<float>(M * K * d.D);
-  w->G = b.take<float>(M * K * d.GH);
+  w->G = b.take<float>(round_up_sz(M, 32) * K * d.GH);  // (whole 32-row blocks: the row-interleaved layout of the tensor-core core)
   w->ld = b.take<float>(M);
   w->flags = b.take<int>(kFlagInts);
   size_t ghmax = 0, xgmax = 0, emax = 0;
@@ -304,7 +304,7 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
 // cond_transform for all K steps, then the c-part of the gate-ih product (models.py:187-190, 206-208)
 static int cond_to_gates(const Dims &d, const lfi_params *p, const float *WcF, const float *cond, size_t M, float *Cact,
                          float *G, int mode, void *gws, size_t gws_bytes, cudaStream_t st, void *cact_hi = nullptr,
-                         void *cact_lo = nullptr) {
+                         void *cact_lo = nullptr, bool g_tiled = false) {
   const int K = d.K, D = d.D, GH = d.GH, In = d.Ci + D;
   GemmArgs g = gemm_args(0, 1, (int)M, K * D, d.Fe, cond, d.Fe, WcF, d.Fe, Cact, K * D, LFI_EPI_BIAS | LFI_EPI_LRELU, p->bc);
   if (cact_hi) { g.pOut = plane_ref(cact_hi, cact_lo, K * D); g.C = nullptr; }  // the activations leave the epilogue as operand planes only
@@ -312,6 +312,7 @@ static int cond_to_gates(const Dims &d, const lfi_params *p, const float *WcF, c
   GemmArgs h = gemm_args(0, 1, (int)M, GH, D, Cact, K * D, p->w_ih + d.Ci, In, G, K * GH, LFI_EPI_BIAS, p->b_ih);
   if (cact_hi) h.pA = plane_ref(cact_hi, cact_lo, K * D, D);
   h.batch = K; h.sA = D; h.sB = (long)GH * In; h.sC = GH; h.sBias = GH;
+  if (g_tiled) { h.c_tiled32 = 1; h.sC = (long)GH * 32; }  // row-interleaved G for the tensor-core flow core (one batch = GH/4 column groups)
   LFI_TRY(gemm_dispatch(mode, h, gws, gws_bytes, st));
   return LFI_OK;
 }
@@ -394,7 +395,8 @@ int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params 
   const float *WcF = (const float *)derived + L.WcF;
 
   LFI_TRY(build_cond(s, d, p, bt, d.start_ts, Tp, w.cond, w.enc, w.gh, true, false, true, gemm_mode, gws, gws_bytes, st));
-  LFI_TRY(cond_to_gates(d, p, WcF, w.cond, M, w.Cact, w.G, gemm_mode, gws, gws_bytes, st, w.cp ? w.cact_hi : nullptr, w.cp ? w.cact_lo : nullptr));
+  LFI_TRY(cond_to_gates(d, p, WcF, w.cond, M, w.Cact, w.G, gemm_mode, gws, gws_bytes, st, w.cp ? w.cact_hi : nullptr, w.cp ? w.cact_lo : nullptr,
+                        w.st_tiled));
 
   core::FwdArgs a;
   memset(&a, 0, sizeof(a));
@@ -407,6 +409,7 @@ int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params 
   a.flags = w.flags; a.flags_bytes = kFlagInts * sizeof(int);
   if (w.cp) { a.py_hi = w.y_hi; a.py_lo = w.y_lo; a.pzf_hi = w.zf_hi; a.pzf_lo = w.zf_lo; a.ph_hi = w.h_hi; a.ph_lo = w.h_lo; }
   a.stash_tiled = w.st_tiled ? 1 : 0;
+  a.g_tiled = w.st_tiled ? 1 : 0;
   return core::launch_fwd(a, st);
 }
 
