@@ -38,6 +38,23 @@ __device__ __forceinline__ void st_release_gpu_t(int *p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 
+constexpr int FNT = 288;  // eight compute warps + the MMA-issue warp
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the eight compute warps
+__device__ __forceinline__ bool csync_and(bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.u32 q, %1, 0;\n\t"
+      "bar.red.and.pred p, 1, 256, q;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r) : "r"((uint32_t)pred) : "memory");
+  return r != 0;
+}
+__device__ __forceinline__ void bar_arrive2() { asm volatile("bar.arrive 2, 288;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void bar_sync2() { asm volatile("bar.sync 2, 288;" ::: "memory"); }
+
 // byte offsets of the operand blocks (all 1024-byte aligned)
 constexpr int kBH = 0;                  // W_hh slice   2 planes x 2 k-blocks x [192 rows x 128 B]   (128-byte swizzle)
 constexpr int kBHPlane = 2 * 192 * 128; //   48 KB per plane, 24 KB per k-block
@@ -52,8 +69,7 @@ constexpr int kAZPlane = 64 * 64;
 constexpr int kF32 = kAZ + 2 * kAZPlane;  // fp32 arrays follow (they also back the aliased rows of the last A block)
 constexpr int kTmemCols = 512;
 constexpr int kColD = 0, kColF = 256;   // accumulators: [0,64) r, [64,128) u, [128,192) n (h side), [192,256) n (i side); LinearZeros
-constexpr int TT = 64;
-__device__ int g_core_timing = 0;  // debug: LFI_CORE_TIMING=1 prints the phase cycle counts of one CTA                  // the thread that issues every MMA (warp 2 holds no accumulator rows)
+__device__ int g_core_timing = 0;  // debug: LFI_CORE_TIMING=1 prints the phase cycle counts of one CTA
 
 struct PlanTC {
   int w, vec, xs, zrow, o, bars, total;  // byte offsets
@@ -77,7 +93,7 @@ __host__ __device__ inline PlanTC plan_tc(const Dims &d) {
 
 }  // namespace
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PNT, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FNT, 1)
 core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) {
   extern __shared__ __align__(16) uint8_t smraw[];
   uint8_t *smb = (uint8_t *)(((uintptr_t)smraw + 1023) & ~(uintptr_t)1023);
@@ -99,7 +115,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
   const bool first = (k == a.k_first), last = (k == a.k_last);
 
   // ---- resident weights: fp32 -> (hi, lo) bf16 planes in the K-major swizzled UMMA layout ------------------------
-  for (int e = tid; e < 192 * 16; e += PNT) {  // W_hh[g*H + 64c + u][8ch .. 8ch+7]
+  for (int e = tid; e < 192 * 16; e += FNT) {  // W_hh[g*H + 64c + u][8ch .. 8ch+7]
     const int n = e >> 4, ch = e & 15, g = n >> 6, u = n & 63;
     const float *src = w.Whh + (size_t)(g * H + PUC * c + u) * H + 8 * ch;
     const float4 v0 = *reinterpret_cast<const float4 *>(src), v1 = *reinterpret_cast<const float4 *>(src + 4);
@@ -111,7 +127,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
     *reinterpret_cast<uint4 *>(smb + kBH + off) = hi;
     *reinterpret_cast<uint4 *>(smb + kBH + kBHPlane + off) = lo;
   }
-  for (int e = tid; e < 192 * 4; e += PNT) {   // W_ih[g*H + 64c + u][8ch .. 8ch+7], zero beyond Ci
+  for (int e = tid; e < 192 * 4; e += FNT) {   // W_ih[g*H + 64c + u][8ch .. 8ch+7], zero beyond Ci
     const int n = e >> 2, ch = e & 3, g = n >> 6, u = n & 63;
     const float *src = w.WihZ + (size_t)(g * H + PUC * c + u) * Cip;
     float v[8];
@@ -124,7 +140,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
     *reinterpret_cast<uint4 *>(smb + kBZ + off) = hi;
     *reinterpret_cast<uint4 *>(smb + kBZ + kBZPlane + off) = lo;
   }
-  for (int e = tid; e < 64 * 8; e += PNT) {    // Wf[j][64c + 8ch .. +7], zero rows beyond Co
+  for (int e = tid; e < 64 * 8; e += FNT) {    // Wf[j][64c + 8ch .. +7], zero rows beyond Co
     const int n = e >> 3, ch = e & 7;
     float v[8];
 #pragma unroll
@@ -135,17 +151,18 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
     *reinterpret_cast<uint4 *>(smb + kBF + off) = hi;
     *reinterpret_cast<uint4 *>(smb + kBF + kBFPlane + off) = lo;
   }
-  for (int e = tid; e < C * (Cp / 4); e += PNT)
+  for (int e = tid; e < C * (Cp / 4); e += FNT)
     *reinterpret_cast<float4 *>(wsm + 4 * e) = *reinterpret_cast<const float4 *>(w.Wfwd + 4 * e);
-  for (int e = tid; e < C; e += PNT) { anb[e] = w.an_bias[e]; ans[e] = expf(w.an_logs[e]); }
-  for (int e = tid; e < 3 * PUC; e += PNT) bhh[e] = w.b_hh[(e / PUC) * H + PUC * c + (e % PUC)];
-  for (int e = tid; e < Co; e += PNT) { bfs[e] = w.bf[e]; e3[e] = expf(3.0f * w.lf[e]); }
-  for (int e = tid; e < 2 * kAZPlane / 16; e += PNT) reinterpret_cast<uint4 *>(smb + kAZ)[e] = make_uint4(0u, 0u, 0u, 0u);
+  for (int e = tid; e < C; e += FNT) { anb[e] = w.an_bias[e]; ans[e] = expf(w.an_logs[e]); }
+  for (int e = tid; e < 3 * PUC; e += FNT) bhh[e] = w.b_hh[(e / PUC) * H + PUC * c + (e % PUC)];
+  for (int e = tid; e < Co; e += FNT) { bfs[e] = w.bf[e]; e3[e] = expf(3.0f * w.lf[e]); }
+  for (int e = tid; e < 2 * kAZPlane / 16; e += FNT) reinterpret_cast<uint4 *>(smb + kAZ)[e] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
     mbar_init(bar_hh, 1); mbar_init(bar_d, 1); mbar_init(bar_f, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+  const bool mma_warp = warp == 8;
+  if (mma_warp) tmem_alloc(tmem_slot, kTmemCols);
   fence_before();
   fence_async_smem();
   cluster.sync();  // both CTAs of the cluster are running before the first distributed-shared-memory access
@@ -175,16 +192,17 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
     float hreg[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) hreg[j] = 0.f;
-    for (int e = tid; e < 2 * kAHPlane / 16; e += PNT) reinterpret_cast<uint4 *>(smb + kAH)[e] = make_uint4(0u, 0u, 0u, 0u);  // state None = zeros
+    for (int e = tid; e < 2 * kAHPlane / 16; e += FNT) reinterpret_cast<uint4 *>(smb + kAH)[e] = make_uint4(0u, 0u, 0u, 0u);  // state None = zeros
     fence_async_smem();
     cluster.sync();
 
     for (int t = 0; t < Tp; ++t, ++it) {
       const size_t cell = (size_t)k * Tp + t;
       const uint32_t ph = (uint32_t)(it & 1);
-      if (timing) tprev = clock64();
-      // ---- 0. recurrent product h_{t-1} W_hh^T: asynchronous on the tensor cores, no dependence on stage k-1 ----------
-      if (tid == TT) {
+      if (mma_warp) {
+        // =================================== MMA-issue warp ===================================
+        if (lane == 0) {  // recurrent product h_{t-1} W_hh^T: no dependence on stage k-1, overlaps the wait for it
+
         fence_after();
         fence_async_smem();
         const uint32_t idesc = idesc_bf16_m128(96);
@@ -204,12 +222,65 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
             }
         }
         umma_commit(bar_hh);
+              }
+        __syncwarp();
+        mbar_wait(bar_hh, ph);  // this CTA's recurrent product has consumed h_{t-1}: the peer may overwrite its half after A
+        cluster_arrive_(); cluster_wait_();  // A: z1 complete in both CTAs
+        if (lane == 0) {
+
+        fence_after();
+        fence_async_smem();
+        const uint32_t id_ru = idesc_bf16_m128(64), id_n = idesc_bf16_m128(32);
+        uint32_t accn = 0;
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr) {
+          const uint32_t pa = (pr == 2) ? kAZPlane : 0, pb = (pr == 1) ? kBZPlane : 0;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const uint64_t ad = make_sdesc(sAZ + pa + ks * 32 - hf * (64 * 64), 512, kSw64);
+              const uint32_t sb = sBZ + pb + hf * (96 * 64) + ks * 32;
+              umma_bf16(tmem + kColD + hf * 96, ad, make_sdesc(sb, 512, kSw64), id_ru, 1u);                        // r, u
+              umma_bf16(tmem + kColD + 192 + hf * 32, ad, make_sdesc(sb + 64 * 64, 512, kSw64), id_n, accn);     // n, input side
+            }
+            accn = 1;
+          }
+        }
+        umma_commit(bar_d);
+              }
+        __syncwarp();
+        bar_sync2();  // gate math done: the new state is in the operand planes
+        if (lane == 0) {
+
+        fence_after();
+        fence_async_smem();
+        const uint32_t idesc = idesc_bf16_m128(32);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr) {
+          const uint32_t pa = (pr == 2) ? kAHPlane : 0, pb = (pr == 1) ? kBFPlane : 0;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)  // output channels 0..31 in lanes 0..63, channels 32..63 in lanes 64..127
+              umma_bf16(tmem + kColF + hf * 32, make_sdesc(sAH + pa + c * (64 * 128) + ks * 32 - hf * (64 * 128), 1024, kSw128),
+                        make_sdesc(sBF + pb + hf * (32 * 128) + ks * 32, 1024, kSw128), idesc, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(bar_f);
+              }
+        __syncwarp();
+        cluster_arrive_(); cluster_wait_();  // B
+        continue;
       }
+      if (timing) tprev = clock64();
       //         request the input if stage k-1 has already published this frame (it usually runs ahead)
       constexpr int XI = (PRH * 64 + PNT - 1) / PNT;  // C <= 64
       float xv[XI];
       bool have_x = first || ld_acquire_gpu_t(wait_flag) > it;
-      have_x = __syncthreads_and(have_x);
+      have_x = csync_and(have_x);
       TSTAMP(0);
       auto fetch_x = [&]() {
 #pragma unroll
@@ -229,7 +300,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
         if (tid == 0) {
           while (ld_acquire_gpu_t(wait_flag) <= it) { }
         }
-        __syncthreads();
+        csync();
         fetch_x();
       }
 #pragma unroll
@@ -246,7 +317,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
           xs[r * pC + cc] = v;
         }
       }
-      __syncthreads();
+      csync();
       TSTAMP(1);
       // ---- 2. invertible 1x1 conv (modules.py:186): z = y @ W, 2 rows x 4 columns per thread (fp32 FFMA) -----------
       {
@@ -273,7 +344,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
               if (4 * cq + j < C) zrow[(2 * rp + i) * pC + 4 * cq + j] = z[i][j];
         }
       }
-      __syncthreads();
+      csync();
       TSTAMP(2);
       if (tid < PRH * 4) {  // z1 of this CTA's rows as operand planes, to both CTAs of the cluster
         const int r = tid >> 2, ch = tid & 3;
@@ -289,32 +360,9 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
         *reinterpret_cast<uint4 *>(peerb + off + kAZPlane) = lo;
       }
       fence_async_smem();
-      if (tid == TT) mbar_wait(bar_hh, ph);  // this CTA's recurrent product has consumed h_{t-1}: the peer may overwrite its half
-      cluster.sync();  // A: z1 complete in both CTAs
+      cluster_arrive_(); cluster_wait_();  // A: z1 complete in both CTAs (the MMA warp joins once its recurrent product is done)
       TSTAMP(3);
       // ---- 3. z1 part of the gate-ih product, then the GRU gate math straight from TMEM -------------------------------
-      if (tid == TT) {
-        fence_after();
-        fence_async_smem();
-        const uint32_t id_ru = idesc_bf16_m128(64), id_n = idesc_bf16_m128(32);
-        uint32_t accn = 0;
-#pragma unroll
-        for (int pr = 0; pr < 3; ++pr) {
-          const uint32_t pa = (pr == 2) ? kAZPlane : 0, pb = (pr == 1) ? kBZPlane : 0;
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const uint64_t ad = make_sdesc(sAZ + pa + ks * 32 - hf * (64 * 64), 512, kSw64);
-              const uint32_t sb = sBZ + pb + hf * (96 * 64) + ks * 32;
-              umma_bf16(tmem + kColD + hf * 96, ad, make_sdesc(sb, 512, kSw64), id_ru, 1u);                        // r, u
-              umma_bf16(tmem + kColD + 192 + hf * 32, ad, make_sdesc(sb + 64 * 64, 512, kSw64), id_n, accn);     // n, input side
-            }
-            accn = 1;
-          }
-        }
-        umma_commit(bar_d);
-      }
       //         gate-ih pre-activations of the first pass (requested here: their issue overlaps the z1 product)
       const size_t gm = (size_t)t * B + row0 + row, gn = (size_t)(k - a.g_k0) * GH + PUC * c + ub;
       const float *Gb = a.g_tiled ? a.G + g_tiled_off(gm, gn, (size_t)a.g_ld) : a.G + gm * a.g_ld + gn;
@@ -378,29 +426,10 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
         fence_async_smem();  // the new state is visible to the tensor cores (of both CTAs)
         TSTAMP(5);
       }
-      __syncthreads();
+      bar_arrive2();  // the MMA warp issues the LinearZeros product
       TSTAMP(6);
 
       // ---- 4. LinearZeros (modules.py:93-95): partial sum over this CTA's 64 hidden units, all 64 rows ---------------
-      if (tid == TT) {
-        fence_after();
-        fence_async_smem();
-        const uint32_t idesc = idesc_bf16_m128(32);
-        uint32_t acc = 0;
-#pragma unroll
-        for (int pr = 0; pr < 3; ++pr) {
-          const uint32_t pa = (pr == 2) ? kAHPlane : 0, pb = (pr == 1) ? kBFPlane : 0;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf)  // output channels 0..31 in lanes 0..63, channels 32..63 in lanes 64..127
-              umma_bf16(tmem + kColF + hf * 32, make_sdesc(sAH + pa + c * (64 * 128) + ks * 32 - hf * (64 * 128), 1024, kSw128),
-                        make_sdesc(sBF + pb + hf * (32 * 128) + ks * 32, 1024, kSw128), idesc, acc);
-            acc = 1;
-          }
-        }
-        umma_commit(bar_f);
-      }
       {  // stash for the backward pass (gates post-activation, h-side n pre-activation, new state) while it runs: tiled
          // layout, the 32 sequences of a warp are contiguous in every store (rows beyond the batch land in the tile's padding)
         const int hs = 2 * half + sub;
@@ -449,7 +478,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
           if (j0 + 4 * i < Cop) *reinterpret_cast<float4 *>(ob + 4 * i) = make_float4(ov[4 * i], ov[4 * i + 1], ov[4 * i + 2], ov[4 * i + 3]);
         fence_before();
       }
-      cluster.sync();  // B: partial sums and the new state are complete in both CTAs
+      cluster_arrive_(); cluster_wait_();  // B: partial sums and the new state are complete in both CTAs
       TSTAMP(7);
 
       // ---- 5. affine coupling (models.py:331-341), log-det, NLL on the last step (modules.py:207-212, models.py:563-565)
@@ -505,13 +534,13 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
           }
         }
       }
-      __syncthreads();
+      csync();
       {
         float *dst = last ? a.z_out + (size_t)t * B * C : a.xin + (cell + Tp) * B * C;  // XIN[k+1][t]
         for (int e = tid; e < nmy * C; e += PNT) { const int r = e / C, j = e - r * C; dst[(size_t)(row0 + lr0 + r) * C + j] = zrow[r * pC + j]; }
       }
       if (!last) {
-        __syncthreads();
+        csync();
         if (tid == 0) st_release_gpu_t(my_flag, it + 1);  // release at gpu scope, cumulative over the CTA barrier above
       }
       TSTAMP(8);
@@ -523,7 +552,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
            stage, it, tacc[0] / it, tacc[1] / it, tacc[2] / it, tacc[3] / it, tacc[4] / it, tacc[5] / it, tacc[6] / it, tacc[7] / it, tacc[8] / it);
   fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (mma_warp) {
     fence_after();
     tmem_dealloc(tmem, kTmemCols);
   }
@@ -552,7 +581,7 @@ int launch_fwd_pipe_tc(const FwdArgs &a, cudaStream_t st) {
   static const int timing = getenv("LFI_CORE_TIMING") ? atoi(getenv("LFI_CORE_TIMING")) : 0;
   if (timing) cudaMemcpyToSymbolAsync(g_core_timing, &timing, sizeof(int), 0, cudaMemcpyHostToDevice, st);
   dim3 grid(2, nk, P);
-  core_fwd_pipe_tc<<<grid, PNT, bytes, st>>>(a, P, ntiles, a.flags);
+  core_fwd_pipe_tc<<<grid, FNT, bytes, st>>>(a, P, ntiles, a.flags);
   LFI_LAUNCH_CHECK();
   return LFI_OK;
 }
