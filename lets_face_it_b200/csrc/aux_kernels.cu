@@ -200,7 +200,10 @@ __global__ void enc_gate_fwd_kernel(EncStep a) {
     const float ng = tanhf(ain + rg * ahn);
     const float h = ng + ug * (hp - ng);
     a.h[idx] = h;
-    if (a.gates) { float *g = a.gates + m * 3 * E; g[e] = rg; g[E + e] = ug; g[2 * E + e] = ng; }
+    if (a.gates && a.gates16) {
+      unsigned short *g = reinterpret_cast<unsigned short *>(a.gates) + m * 3 * E;
+      g[e] = q_unorm16(rg); g[E + e] = q_unorm16(ug); g[2 * E + e] = q_snorm16(ng);
+    } else if (a.gates) { float *g = a.gates + m * 3 * E; g[e] = rg; g[E + e] = ug; g[2 * E + e] = ng; }
     if (a.ahn) a.ahn[idx] = ahn;
     if (a.cond) a.cond[m * a.cond_ld + e] = h;
     if (a.h_hi) {
@@ -260,7 +263,13 @@ __global__ void enc_gate_bwd2_kernel(EncStepBwd2 a, int rows_per_block) {
     const size_t idx = (size_t)m * E + e, g3 = (size_t)m * 3 * E;
     float dh = a.dh[idx];
     if (a.dh_extra) dh += a.dh_extra[(size_t)m * a.dh_extra_ld + e];
-    const float rg = a.gates[g3 + e], ug = a.gates[g3 + E + e], ng = a.gates[g3 + 2 * E + e];
+    float rg, ug, ng;
+    if (a.gates16) {
+      const unsigned short *gq = reinterpret_cast<const unsigned short *>(a.gates);
+      rg = dq_unorm16(gq[g3 + e]); ug = dq_unorm16(gq[g3 + E + e]); ng = dq_snorm16(gq[g3 + 2 * E + e]);
+    } else {
+      rg = a.gates[g3 + e]; ug = a.gates[g3 + E + e]; ng = a.gates[g3 + 2 * E + e];
+    }
     const float hp = a.hprev ? a.hprev[idx] : 0.f;
     const float an = a.ahn[idx];
     const float dn = dh * (1.0f - ug), du = dh * (hp - ng);
@@ -297,8 +306,19 @@ __global__ void __launch_bounds__(256) enc_gate_bwd2_v4_kernel(EncStepBwd2 a) {
   for (int m = blockIdx.x * rpb + rl; m < a.M; m += gridDim.x * rpb) {
     const size_t idx = (size_t)m * E + e, g3 = (size_t)m * 3 * E + e;
     float4 d4 = *reinterpret_cast<const float4 *>(a.dh + idx);
-    const float4 r4 = __ldg(reinterpret_cast<const float4 *>(a.gates + g3)), u4 = __ldg(reinterpret_cast<const float4 *>(a.gates + g3 + E)),
-                 n4 = __ldg(reinterpret_cast<const float4 *>(a.gates + g3 + 2 * E)), a4 = __ldg(reinterpret_cast<const float4 *>(a.ahn + idx));
+    float4 r4, u4, n4;
+    if (a.gates16) {
+      const unsigned short *gq = reinterpret_cast<const unsigned short *>(a.gates);
+      const uint2 rq = __ldg(reinterpret_cast<const uint2 *>(gq + g3)), uq = __ldg(reinterpret_cast<const uint2 *>(gq + g3 + E)),
+                  nq = __ldg(reinterpret_cast<const uint2 *>(gq + g3 + 2 * E));
+      r4 = make_float4(dq_unorm16(rq.x & 0xffff), dq_unorm16(rq.x >> 16), dq_unorm16(rq.y & 0xffff), dq_unorm16(rq.y >> 16));
+      u4 = make_float4(dq_unorm16(uq.x & 0xffff), dq_unorm16(uq.x >> 16), dq_unorm16(uq.y & 0xffff), dq_unorm16(uq.y >> 16));
+      n4 = make_float4(dq_snorm16(nq.x & 0xffff), dq_snorm16(nq.x >> 16), dq_snorm16(nq.y & 0xffff), dq_snorm16(nq.y >> 16));
+    } else {
+      r4 = __ldg(reinterpret_cast<const float4 *>(a.gates + g3)); u4 = __ldg(reinterpret_cast<const float4 *>(a.gates + g3 + E));
+      n4 = __ldg(reinterpret_cast<const float4 *>(a.gates + g3 + 2 * E));
+    }
+    const float4 a4 = __ldg(reinterpret_cast<const float4 *>(a.ahn + idx));
     const float4 h4 = a.hprev ? __ldg(reinterpret_cast<const float4 *>(a.hprev + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (a.dh_extra) {
       const float4 x4 = *reinterpret_cast<const float4 *>(a.dh_extra + (size_t)m * a.dh_extra_ld + e);

@@ -41,6 +41,7 @@ struct EncStep {
   float *cond; int cond_ld;  // final step: also written to cond[m*cond_ld + e] (nullable)
   void *h_hi, *h_lo;    // optional bf16 planes of h [M][E] (tensor-core modes: next step's GEMM operand, dW_hh operand)
   int s, hist, B, T, Tp, t0, E;
+  int gates16;          // gates stash in 16-bit fixed point (lfi_common.cuh: q_unorm16 / q_snorm16)
 };
 int enc_gate_fwd(const EncStep &a, cudaStream_t st);
 
@@ -65,6 +66,7 @@ struct EncStepBwd2 {
   void *dah_hi, *dah_lo, *dan_hi, *dan_lo;   // bf16 plane outputs (nullable; lo nullable)
   float *gb_ih, *gb_hh;                      // [3E] bias gradients, accumulated
   int M, E;
+  int gates16;                               // gates stash in 16-bit fixed point
 };
 int enc_gate_bwd2(const EncStepBwd2 &a, cudaStream_t st);
 

@@ -314,7 +314,12 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
         }
         const size_t o1 = (size_t)m * E + e, o3 = (size_t)m * 3 * E + e;
         st4(G.h + o1, hn[0], hn[1], hn[2], hn[3]);
-        if (G.gates && !(p.dbg & 1)) {
+        if (G.gates && G.gates16) {
+          unsigned short *gq = reinterpret_cast<unsigned short *>(G.gates);
+          *reinterpret_cast<uint2 *>(gq + o3) = make_uint2(q_unorm16(rg[0]) | ((uint32_t)q_unorm16(rg[1]) << 16), q_unorm16(rg[2]) | ((uint32_t)q_unorm16(rg[3]) << 16));
+          *reinterpret_cast<uint2 *>(gq + o3 + E) = make_uint2(q_unorm16(ug[0]) | ((uint32_t)q_unorm16(ug[1]) << 16), q_unorm16(ug[2]) | ((uint32_t)q_unorm16(ug[3]) << 16));
+          *reinterpret_cast<uint2 *>(gq + o3 + 2 * E) = make_uint2(q_snorm16(ng[0]) | ((uint32_t)q_snorm16(ng[1]) << 16), q_snorm16(ng[2]) | ((uint32_t)q_snorm16(ng[3]) << 16));
+        } else if (G.gates && !(p.dbg & 1)) {
           st4(G.gates + o3, rg[0], rg[1], rg[2], rg[3]);
           st4(G.gates + o3 + E, ug[0], ug[1], ug[2], ug[3]);
           st4(G.gates + o3 + 2 * E, ng[0], ng[1], ng[2], ng[3]);

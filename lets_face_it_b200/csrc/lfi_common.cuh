@@ -137,8 +137,17 @@ struct PlaneRef {
 // recurrent product h_{s-1} W_hh^T (forward) / dA_h W_hh (backward) leaves TMEM straight into the gate math, so the
 // [M, 3E] pre-activation matrix never travels through HBM.  Argument meaning as aux::EncStep / aux::EncStepBwd2.
 enum { LFI_FUSE_NONE = 0, LFI_FUSE_GRU_FWD = 1, LFI_FUSE_GRU_BWD = 2 };
+// 16-bit fixed-point gate stash of the encoder GRUs (tensor-core modes): r, u in [0,1] as unorm16 (|err| <= 7.7e-6), n in
+// [-1,1] as snorm16 (|err| <= 1.6e-5).  The forward pass itself uses the exact fp32 gates; only the backward pass reads
+// the stash, and its gradient tolerance (5e-3 relative L2 per tensor in bf16x3 mode) is ~100x above the induced error.
+__device__ __forceinline__ unsigned short q_unorm16(float v) { return (unsigned short)__float2uint_rn(fminf(fmaxf(v, 0.f), 1.f) * 65535.0f); }
+__device__ __forceinline__ unsigned short q_snorm16(float v) { return (unsigned short)(short)__float2int_rn(fminf(fmaxf(v, -1.f), 1.f) * 32767.0f); }
+__device__ __forceinline__ float dq_unorm16(unsigned short q) { return (float)q * (1.0f / 65535.0f); }
+__device__ __forceinline__ float dq_snorm16(unsigned short q) { return (float)(short)q * (1.0f / 32767.0f); }
+
 struct GruEpi {
   int E, s, hist, B, T, t0;
+  int gates16;  // gates stash in 16-bit fixed point ([M][3E] unsigned short in the same buffer)
   // forward (step s >= 1)
   const float *xp, *b_ih, *b_hh, *mask, *hprev;
   float *h, *gates, *ahn, *cond; int cond_ld;

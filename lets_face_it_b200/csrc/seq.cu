@@ -78,6 +78,7 @@ struct EncWs {
   float *ahn;    // [hist][M][E]   (training only)
   // tensor-core modes (planes == true): bf16 operand planes written by the producers themselves, never re-split
   bool planes;
+  bool gates16;           // gates stash in 16-bit fixed point (planes mode; the fp32 mode keeps exact fp32 gates)
   void *hp_hi, *hp_lo;    // h          [hist | 2][M][E]
   void *whh_hi, *whh_lo;  // W_hh       [3E][E]  (K-major B of the step GEMM, MN-major B of dh_prev = dA_h W_hh)
   // backward (training only): gate gradients of every window step, kept for the batched weight-gradient GEMMs
@@ -141,6 +142,7 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
     e.gates = b.take<float>(h * M * 3 * E);
     e.ahn = b.take<float>(h * M * E);
     e.planes = enc_use_planes(s, m, M, mode);
+    e.gates16 = e.planes && E % 4 == 0 && env_flag("LFI_GATES16", true) && !env_flag("LFI_FUSED_GRU_BWD", false);
     if (e.planes) {
       const bool lo = mode == LFI_GEMM_BF16X3;
       const size_t dimp = round_up(s->dim[m], 8);
@@ -259,6 +261,7 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
       a.h_hi = ew.planes ? (void *)((uint16_t *)ew.hp_hi + (size_t)cur * M * E) : nullptr;
       a.h_lo = (ew.planes && lo) ? (void *)((uint16_t *)ew.hp_lo + (size_t)cur * M * E) : nullptr;
       a.s = sidx; a.hist = hist; a.B = B; a.T = T; a.Tp = Tp; a.t0 = t0; a.E = E;
+      a.gates16 = (stash && ew.gates16) ? 1 : 0;
       if (fused) {
         // recurrent product and gate math in one launch: the [M, 3E] pre-activations stay in TMEM
         GemmArgs gg = gemm_args(0, 1, (int)M, 3 * E, E, nullptr, E, nullptr, E, nullptr, 3 * E);
@@ -266,7 +269,7 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
         gg.pB = plane_ref(ew.whh_hi, ew.whh_lo, E);
         gg.fuse = LFI_FUSE_GRU_FWD;
         GruEpi &q = gg.gru;
-        q.E = E; q.s = sidx; q.hist = hist; q.B = B; q.T = T; q.t0 = t0;
+        q.E = E; q.s = sidx; q.hist = hist; q.B = B; q.T = T; q.t0 = t0; q.gates16 = a.gates16;
         q.xp = a.xp; q.b_ih = a.b_ih; q.b_hh = a.b_hh; q.mask = a.mask; q.hprev = a.hprev;
         q.h = a.h; q.gates = a.gates; q.ahn = a.ahn; q.cond = a.cond; q.cond_ld = a.cond_ld; q.h_hi = a.h_hi; q.h_lo = a.h_lo;
         LFI_TRY(gemm_dispatch(mode, gg, gws, gws_bytes, cs));
@@ -561,7 +564,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
       } else {
         e.dah32 = ew.dah32 + (size_t)sidx * M * 3 * E; e.dan32 = ew.dan32 + (size_t)sidx * M * E;
       }
-      e.gb_ih = g->enc_b_ih[m]; e.gb_hh = g->enc_b_hh[m]; e.M = (int)M; e.E = E;
+      e.gb_ih = g->enc_b_ih[m]; e.gb_hh = g->enc_b_hh[m]; e.M = (int)M; e.E = E; e.gates16 = ew.gates16 ? 1 : 0;
       if (!fused || sidx == hist - 1) LFI_TRY(aux::enc_gate_bwd2(e, st));
       if (sidx) {  // dh_{s-1} += dA_h W_hh
         GemmArgs t = gemm_args(0, 0, (int)M, E, 3 * E, e.dah32, 3 * E, p->enc_w_hh[m], E, ew.dhe, E, LFI_EPI_ACCUM);
