@@ -1,0 +1,16 @@
+"""Gradient error induced by the 16-bit gate stash of the encoder GRUs (LFI_GATES16=1 vs 0), bf16x3 mode."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests.helpers import final_hparams
+from tests.kat import build_kat_model, kat_batch, to_device
+from lets_face_it_b200 import _cabi as cabi
+hp = final_hparams()
+m = build_kat_model(hp, "cuda:0"); m.glow.set_actnorm_init(True); m.gemm_mode = cabi.GEMM_BF16X3; m.train()
+batch = to_device(kat_batch(hp, 256, 80, seed=14), "cuda:0")
+def run():
+    m.zero_grad(); z, loss, _ = m(batch); loss.backward(); torch.cuda.synchronize()
+    return {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+os.environ["LFI_GATES16"] = "0"; g0 = run()
+os.environ["LFI_GATES16"] = "1"; g1 = run()
+worst = sorted(((float((g1[k].double() - g0[k].double()).norm() / g0[k].double().norm().clamp_min(1e-30)), k) for k in g0), reverse=True)
+for e, k in worst[:6]: print("%.3e  %s" % (e, k))
