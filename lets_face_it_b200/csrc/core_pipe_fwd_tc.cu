@@ -309,10 +309,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
         if (e < PRH * C) {
           float v = 0.f;
           if (r < nmy) {
-            const int b = row0 + lr0 + r;
             v = (xv[i] + anb[cc]) * ans[cc];
-            if (a.st_y) a.st_y[(cell * B + b) * C + cc] = v;
-            if (a.py_hi) put_plane(a.py_hi, a.py_lo, (cell * B + b) * C + cc, v);
           }
           xs[r * pC + cc] = v;
         }
@@ -360,7 +357,15 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
         *reinterpret_cast<uint4 *>(peerb + off + kAZPlane) = lo;
       }
       fence_async_smem();
-      cluster_arrive_(); cluster_wait_();  // A: z1 complete in both CTAs (the MMA warp joins once its recurrent product is done)
+      cluster_arrive_();  // A: z1 complete in both CTAs (the MMA warp joins once its recurrent product is done)
+      for (int e = tid; e < nmy * C; e += PNT) {  // y stash of this CTA's rows (fp32 and operand planes) inside the barrier window
+        const int r = e / C, j = e - r * C;
+        const size_t o = (cell * B + row0 + lr0 + r) * C + j;
+        const float yv = xs[r * pC + j];
+        if (a.st_y) a.st_y[o] = yv;
+        if (a.py_hi) put_plane(a.py_hi, a.py_lo, o, yv);
+      }
+      cluster_wait_();
       TSTAMP(3);
       // ---- 3. z1 part of the gate-ih product, then the GRU gate math straight from TMEM -------------------------------
       //         gate-ih pre-activations of the first pass (requested here: their issue overlaps the z1 product)
@@ -373,13 +378,6 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
       for (int g = 0; g < 3; ++g)
 #pragma unroll
         for (int i = 0; i < 4; ++i) gq[g][i] = rowok ? __ldg(reinterpret_cast<const float4 *>(Gb + g * gstep_g + i * gstep_i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int e = tid; e < nmy * C; e += PNT) {  // zf stash of this CTA's rows (fp32 and operand planes) while the product runs
-        const int r = e / C, j = e - r * C;
-        const size_t o = (cell * B + row0 + lr0 + r) * C + j;
-        const float zv = zrow[r * pC + j];
-        if (a.st_zf) a.st_zf[o] = zv;
-        if (a.pzf_hi) put_plane(a.pzf_hi, a.pzf_lo, o, zv);
-      }
       float vr[16], vu[16], vh[16], vi[16];
       uint4 hi0, lo0, hi1, lo1;
       {
@@ -442,6 +440,25 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
             *reinterpret_cast<float4 *>(gp + 2048 + i * 256) = make_float4(vi[4 * i], vi[4 * i + 1], vi[4 * i + 2], vi[4 * i + 3]);
           }
         }
+      }
+      {
+        mbar_wait(bar_f, ph);
+        fence_after();
+        float ov[16];
+        tmem_ld16(tlane + kColF + half * 32 + 16 * sub, ov);
+        tmem_ld_wait();
+        const int dest = row >> 5, lr = row & 31;  // CTA that owns this row; slot c holds this CTA's partial
+        const int j0 = 32 * half + 16 * sub;
+        float *ob = (float *)((dest == c ? smb : peerb) + pl.o) + c * PRH * pO + lr * pO + j0;
+        const int Cop = d.Cop;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (j0 + 4 * i < Cop) *reinterpret_cast<float4 *>(ob + 4 * i) = make_float4(ov[4 * i], ov[4 * i + 1], ov[4 * i + 2], ov[4 * i + 3]);
+        fence_before();
+      }
+      cluster_arrive_();  // B: partial sums and the new state are complete in both CTAs
+      {  // rest of the backward stash (h-side n pre-activation, new state, operand planes, zf) inside the barrier window
+        const int hs = 2 * half + sub;
         if (a.st_ahn) {
           float *ap = a.st_ahn + stash_tiled_off(cell, ntiles, tile, c, hs, 1, 0, 0) + 4 * row;
 #pragma unroll
@@ -463,22 +480,14 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
           }
         }
       }
-      {
-        mbar_wait(bar_f, ph);
-        fence_after();
-        float ov[16];
-        tmem_ld16(tlane + kColF + half * 32 + 16 * sub, ov);
-        tmem_ld_wait();
-        const int dest = row >> 5, lr = row & 31;  // CTA that owns this row; slot c holds this CTA's partial
-        const int j0 = 32 * half + 16 * sub;
-        float *ob = (float *)((dest == c ? smb : peerb) + pl.o) + c * PRH * pO + lr * pO + j0;
-        const int Cop = d.Cop;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (j0 + 4 * i < Cop) *reinterpret_cast<float4 *>(ob + 4 * i) = make_float4(ov[4 * i], ov[4 * i + 1], ov[4 * i + 2], ov[4 * i + 3]);
-        fence_before();
+      for (int e = tid; e < nmy * C; e += PNT) {  // zf stash of this CTA's rows (fp32 and operand planes) 
+        const int r = e / C, j = e - r * C;
+        const size_t o = (cell * B + row0 + lr0 + r) * C + j;
+        const float zv = zrow[r * pC + j];
+        if (a.st_zf) a.st_zf[o] = zv;
+        if (a.pzf_hi) put_plane(a.pzf_hi, a.pzf_lo, o, zv);
       }
-      cluster_arrive_(); cluster_wait_();  // B: partial sums and the new state are complete in both CTAs
+      cluster_wait_();
       TSTAMP(7);
 
       // ---- 5. affine coupling (models.py:331-341), log-det, NLL on the last step (modules.py:207-212, models.py:563-565)
