@@ -124,6 +124,56 @@ class Trainer:
         return torch.sqrt(self.scratch[0]) / self.world
 
 
+class HostFeed:
+    """End-to-end driver over host batches (what a DataLoader with pinned memory hands to `LetsFaceItGlow.training_step`):
+    every step's inputs are copied host -> device on a copy stream into one of two device buffers while the previous step
+    computes, and every step's loss is read back (device -> host) one step late, so that neither the copy nor the read-back
+    leaves the GPU idle.  `step(host_batch)` returns the loss (python float) of the PREVIOUS call (None on the first);
+    `flush()` returns the last one."""
+
+    def __init__(self, trainer):
+        self.tr = trainer
+        dev = trainer.eng.theta.device
+        self.dev = dev
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.bufs = [None, None]
+        self.copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self.consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.i = 0
+        self.pending = None  # (pinned host scalar, event) of the previous step's loss
+        self._loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def step(self, host_batch, masks=None):
+        j = self.i & 1
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            if self.i >= 2:
+                self.copy_stream.wait_event(self.consumed[j])  # the step that last read this buffer is done
+            if self.bufs[j] is None or any(self.bufs[j][k].shape != v.shape for k, v in host_batch.items()):
+                self.bufs[j] = {k: torch.empty(v.shape, dtype=torch.float32, device=self.dev) for k, v in host_batch.items()}
+            for k, v in host_batch.items():
+                self.bufs[j][k].copy_(v, non_blocking=True)
+            self.copied[j].record(self.copy_stream)
+        cur.wait_event(self.copied[j])
+        loss = self.tr.step(self.bufs[j], masks)
+        self.consumed[j].record(cur)
+        self._loss_host[j].copy_(loss.detach().reshape(1), non_blocking=True)
+        self._loss_ev[j].record(cur)
+        prev = self.flush() if self.pending is not None else None
+        self.pending = j
+        self.i += 1
+        return prev
+
+    def flush(self):
+        """Loss of the most recent step whose read-back has not been returned yet."""
+        if self.pending is None:
+            return None
+        j, self.pending = self.pending, None
+        self._loss_ev[j].synchronize()
+        return float(self._loss_host[j][0])
+
+
 def allreduce_flat_gradient(g, world, group=None):
     """The one exchange of the path: SUM all-reduce of the flat fp32 gradient over the ranks.
     The mean over the global batch is restored by `grad_scale = 1/world` in the fused clip+Adam (every rank holds an

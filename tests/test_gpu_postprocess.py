@@ -68,3 +68,21 @@ def test_training_step_probe_and_loss_scale():
     state = random.getstate()
     _, deranged = tr.training_step(batch)
     assert not deranged and random.getstate() == state
+
+
+def test_host_feed_matches_device_steps():
+    """`HostFeed` (pinned host batch -> copy stream -> step, loss read back one step late) returns exactly the losses of
+    `Trainer.step` on device-resident copies of the same batches, in order."""
+    from lets_face_it_b200.train import HostFeed, Trainer
+
+    hp = final_hparams()
+    m = build_kat_model(hp, DEV)
+    m.glow.set_actnorm_init(True)
+    m.train()
+    tr = Trainer(m, dropout=False, lr=0.0)
+    hosts = [{k: v.pin_memory() for k, v in kat_batch(hp, 16, 40, seed=40 + i).items()} for i in range(4)]
+    want = [float(tr.step(to_device(h, DEV))) for h in hosts]
+    feed = HostFeed(tr)
+    got = [feed.step(h) for h in hosts] + [feed.flush()]
+    assert got[0] is None and feed.flush() is None
+    assert got[1:] == pytest.approx(want, rel=1e-6)
