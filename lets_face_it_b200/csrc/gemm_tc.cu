@@ -218,6 +218,29 @@ __device__ __forceinline__ TileCoord tile_coord(const Params &p, int tile, int n
 
 // ---- fused encoder-GRU epilogues ---------------------------------------------------------------------
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+// L2 residency control for the fused encoder-GRU epilogue: the input projections xp (63 MB, re-read by every window step)
+// are kept (evict_last) while the write-once stash streams through (evict_first)
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ld4_hint(const float *p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st4_hint(float *p, float a, float b, float c, float d, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st2u_hint(void *p, uint2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) { *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d); }
 __device__ __forceinline__ void st_planes4(__nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t o, const float (&v)[4]) {
   __align__(8) __nv_bfloat16 h4[4], l4[4];
@@ -262,6 +285,7 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
   const int u_base = (t.n0 / 192) * 64;
   const int mrow0 = t.m0 + q * 32;
   __nv_bfloat16 *hhi = (__nv_bfloat16 *)G.h_hi, *hlo = (__nv_bfloat16 *)G.h_lo;
+  const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
   bool waited = false;
   for (int sc = half; sc < 4; sc += 2) {
     const int e = min(u_base + 16 * sc + cg, E - 4);
@@ -275,7 +299,7 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
       if (p.dbg & 4) { mk[i] = 1.f; xr[i] = xu[i] = xn[i] = hp[i] = make_float4(0.1f, 0.2f, 0.3f, 0.4f); continue; }
       mk[i] = G.mask ? G.mask[(size_t)m * G.hist + G.s] : 1.0f;
       const float *xp = G.xp + ((size_t)b * G.T + tau) * 3 * E + e;
-      xr[i] = ld4(xp); xu[i] = ld4(xp + E); xn[i] = ld4(xp + 2 * E);
+      xr[i] = ld4_hint(xp, pol_keep); xu[i] = ld4_hint(xp + E, pol_keep); xn[i] = ld4_hint(xp + 2 * E, pol_keep);
       hp[i] = ld4(G.hprev + (size_t)m * E + e);
     }
     const float4 bir = __ldg(reinterpret_cast<const float4 *>(G.b_ih + e)), biu = __ldg(reinterpret_cast<const float4 *>(G.b_ih + E + e)),
@@ -316,15 +340,15 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
         st4(G.h + o1, hn[0], hn[1], hn[2], hn[3]);
         if (G.gates && G.gates16) {
           unsigned short *gq = reinterpret_cast<unsigned short *>(G.gates);
-          *reinterpret_cast<uint2 *>(gq + o3) = make_uint2(q_unorm16(rg[0]) | ((uint32_t)q_unorm16(rg[1]) << 16), q_unorm16(rg[2]) | ((uint32_t)q_unorm16(rg[3]) << 16));
-          *reinterpret_cast<uint2 *>(gq + o3 + E) = make_uint2(q_unorm16(ug[0]) | ((uint32_t)q_unorm16(ug[1]) << 16), q_unorm16(ug[2]) | ((uint32_t)q_unorm16(ug[3]) << 16));
-          *reinterpret_cast<uint2 *>(gq + o3 + 2 * E) = make_uint2(q_snorm16(ng[0]) | ((uint32_t)q_snorm16(ng[1]) << 16), q_snorm16(ng[2]) | ((uint32_t)q_snorm16(ng[3]) << 16));
+          st2u_hint(gq + o3, make_uint2(q_unorm16(rg[0]) | ((uint32_t)q_unorm16(rg[1]) << 16), q_unorm16(rg[2]) | ((uint32_t)q_unorm16(rg[3]) << 16)), pol_stream);
+          st2u_hint(gq + o3 + E, make_uint2(q_unorm16(ug[0]) | ((uint32_t)q_unorm16(ug[1]) << 16), q_unorm16(ug[2]) | ((uint32_t)q_unorm16(ug[3]) << 16)), pol_stream);
+          st2u_hint(gq + o3 + 2 * E, make_uint2(q_snorm16(ng[0]) | ((uint32_t)q_snorm16(ng[1]) << 16), q_snorm16(ng[2]) | ((uint32_t)q_snorm16(ng[3]) << 16)), pol_stream);
         } else if (G.gates && !(p.dbg & 1)) {
           st4(G.gates + o3, rg[0], rg[1], rg[2], rg[3]);
           st4(G.gates + o3 + E, ug[0], ug[1], ug[2], ug[3]);
           st4(G.gates + o3 + 2 * E, ng[0], ng[1], ng[2], ng[3]);
         }
-        if (G.ahn && !(p.dbg & 1)) st4(G.ahn + o1, ah[0], ah[1], ah[2], ah[3]);
+        if (G.ahn && !(p.dbg & 1)) st4_hint(G.ahn + o1, ah[0], ah[1], ah[2], ah[3], pol_stream);
         if (G.cond) {
           float *cd = G.cond + (size_t)m * G.cond_ld + e;
           if (p.cond_vec) st4(cd, hn[0], hn[1], hn[2], hn[3]);
