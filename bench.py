@@ -91,29 +91,41 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []  # (timestamp or None, sm, max, reasons)
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    if window is not None:
-                        ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                        if ts < window[0] - 0.05 or ts > window[1] + 0.05:
-                            continue
-                    sm.append(float(f[1])); mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    smv, mxv = float(f[1]), float(f[2])
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                rs = {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9])
+                      if v.lower().startswith("active")}
+                rows.append((ts, smv, mxv, rs))
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        sel, note = rows, None
+        if window is not None and rows:
+            # samples inside the timed region; a short region (10 steps ~ 0.12 s) can fall between two 50 ms polls when several
+            # ranks query at once, so the margin widens (the GPU is under the same load right before / after: warm-up, e2e leg)
+            for margin in (0.05, 0.3, 1.0):
+                sel = [r for r in rows if window[0] - margin <= r[0] <= window[1] + margin]
+                if sel:
+                    note = None if margin == 0.05 else "no poll inside the timed region: samples within %.1f s of it" % margin
+                    break
+            if not sel:
+                mid = 0.5 * (window[0] + window[1])
+                sel, note = [min(rows, key=lambda r: abs(r[0] - mid))], "nearest poll to the timed region"
+        if sel:
+            sm = sorted(r[1] for r in sel)
+            reasons = set().union(*[r[3] for r in sel])
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[2] for r in sel), "reasons": sorted(reasons), "samples": len(sel)}
+            if note:
+                out["note"] = note
         return out
 
 
