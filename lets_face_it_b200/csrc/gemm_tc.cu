@@ -872,7 +872,7 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   p.splitk = 1;
   const long tiles = (long)((p.tiles_m + CL - 1) / CL) * CL * p.tiles_n * g.batch;  // CTA tiles (pairs: incl. an empty half)
   if (g.epi == LFI_EPI_ACCUM && tiles * 2 <= g_sms && nkb >= 16) {
-    int sk = (int)((g_sms + tiles - 1) / tiles);
+    int sk = (int)(g_sms / tiles);  // floor: tiles * sk must not spill into a second wave (6 tiles x 25 splits = 150 CTAs did)
     if (sk > nkb / 8) sk = nkb / 8;
     if (sk < 1) sk = 1;
     // every split must own at least one k-block
