@@ -861,6 +861,13 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
     const long ptiles = (long)(((g.M + BM - 1) / BM + 1) / 2) * ((g.N + bn2 - 1) / bn2) * g.batch;
     if (g.M > BM && ptiles >= g_sms / 2) { pair = true; p.bn = bn2; }
   }
+  if (!pair && g.fuse == LFI_FUSE_NONE && p.bn == 256 && g.N % 128 == 0) {
+    // one 128 x 256 tile per CTA and fewer tiles than SMs: the launch is the serial latency of one tile (loads -> MMAs -> epilogue).
+    // Half-width tiles give every CTA two or more, so that the mainloop of one overlaps the epilogue of the previous.
+    static const bool narrow_on = env_flag("LFI_GEMM_NARROW", true);
+    const long t256 = (long)((g.M + BM - 1) / BM) * ((g.N + 255) / 256) * g.batch;
+    if (narrow_on && t256 < g_sms && t256 * 2 > g_sms) p.bn = 128;
+  }
   const int CL = pair ? 2 : 1;
   p.tiles_m = (g.M + BM - 1) / BM; p.tiles_n = (g.N + p.bn - 1) / p.bn;
   const int stage_bytes = nplanes * (BM * BK * 2 + (p.bn / CL) * BK * 2);  // per CTA
