@@ -57,7 +57,6 @@ struct Params {
   float *colsum; long sColsum;                          // += column sums of the final values
   int c_tiled;  // row-interleaved C (GemmArgs::c_tiled32)
   int fuse;     // LFI_FUSE_*
-  int dbg;
   int cond_vec; // fused GRU forward: the cond slice allows 128-bit stores
   GruEpi gru;
 };
@@ -296,7 +295,6 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
       const int m = min(mrow0 + rr + 8 * i, p.M - 1);
       const int b = m % G.B, tp = m / G.B;
       const int tau = G.t0 + tp - G.hist + 1 + G.s;
-      if (p.dbg & 4) { mk[i] = 1.f; xr[i] = xu[i] = xn[i] = hp[i] = make_float4(0.1f, 0.2f, 0.3f, 0.4f); continue; }
       mk[i] = G.mask ? G.mask[(size_t)m * G.hist + G.s] : 1.0f;
       const float *xp = G.xp + ((size_t)b * G.T + tau) * 3 * E + e;
       xr[i] = ld4_hint(xp, pol_keep); xu[i] = ld4_hint(xp + E, pol_keep); xn[i] = ld4_hint(xp + 2 * E, pol_keep);
@@ -308,13 +306,9 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
                  bhn = __ldg(reinterpret_cast<const float4 *>(G.b_hh + 2 * E + e));
     if (!waited) { mbar_wait(tfull, aph); tc_fence_after(); waited = true; }
     float ar[4][4], au[4][4], an[4][4];
-    if (!(p.dbg & 16)) {
     chunk_to_rows(tbase + sc * 16, stg, lane, rr, cg, ar);
     chunk_to_rows(tbase + 64 + sc * 16, stg, lane, rr, cg, au);
     chunk_to_rows(tbase + 128 + sc * 16, stg, lane, rr, cg, an);
-    } else {
-      for (int i = 0; i < 4; ++i) for (int c = 0; c < 4; ++c) { ar[i][c] = 0.1f * i; au[i][c] = 0.2f * c; an[i][c] = 0.3f; }
-    }
     if (u_base + 16 * sc + cg >= E) continue;
     const float bir_[4] = {bir.x, bir.y, bir.z, bir.w}, biu_[4] = {biu.x, biu.y, biu.z, biu.w}, bin_[4] = {bin.x, bin.y, bin.z, bin.w};
     const float bhr_[4] = {bhr.x, bhr.y, bhr.z, bhr.w}, bhu_[4] = {bhu.x, bhu.y, bhu.z, bhu.w}, bhn_[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
@@ -330,10 +324,9 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
           const float air = mk[i] * xr_[c] + bir_[c], aiu = mk[i] * xu_[c] + biu_[c], ain = mk[i] * xn_[c] + bin_[c];
           const float ahr = bhr_[c] + ar[i][c], ahu = bhu_[c] + au[i][c];
           ah[c] = bhn_[c] + an[i][c];
-          if (p.dbg & 8) { rg[c] = air + ahr; ug[c] = aiu + ahu; ng[c] = ain + rg[c] * ah[c]; } else {
           rg[c] = fast_sigmoid(air + ahr);
           ug[c] = fast_sigmoid(aiu + ahu);
-          ng[c] = fast_tanh(ain + rg[c] * ah[c]); }
+          ng[c] = fast_tanh(ain + rg[c] * ah[c]);
           hn[c] = ng[c] + ug[c] * (hp_[c] - ng[c]);
         }
         const size_t o1 = (size_t)m * E + e, o3 = (size_t)m * 3 * E + e;
@@ -343,18 +336,18 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
           st2u_hint(gq + o3, make_uint2(q_unorm16(rg[0]) | ((uint32_t)q_unorm16(rg[1]) << 16), q_unorm16(rg[2]) | ((uint32_t)q_unorm16(rg[3]) << 16)), pol_stream);
           st2u_hint(gq + o3 + E, make_uint2(q_unorm16(ug[0]) | ((uint32_t)q_unorm16(ug[1]) << 16), q_unorm16(ug[2]) | ((uint32_t)q_unorm16(ug[3]) << 16)), pol_stream);
           st2u_hint(gq + o3 + 2 * E, make_uint2(q_snorm16(ng[0]) | ((uint32_t)q_snorm16(ng[1]) << 16), q_snorm16(ng[2]) | ((uint32_t)q_snorm16(ng[3]) << 16)), pol_stream);
-        } else if (G.gates && !(p.dbg & 1)) {
+        } else if (G.gates) {
           st4(G.gates + o3, rg[0], rg[1], rg[2], rg[3]);
           st4(G.gates + o3 + E, ug[0], ug[1], ug[2], ug[3]);
           st4(G.gates + o3 + 2 * E, ng[0], ng[1], ng[2], ng[3]);
         }
-        if (G.ahn && !(p.dbg & 1)) st4_hint(G.ahn + o1, ah[0], ah[1], ah[2], ah[3], pol_stream);
+        if (G.ahn) st4_hint(G.ahn + o1, ah[0], ah[1], ah[2], ah[3], pol_stream);
         if (G.cond) {
           float *cd = G.cond + (size_t)m * G.cond_ld + e;
           if (p.cond_vec) st4(cd, hn[0], hn[1], hn[2], hn[3]);
           else { cd[0] = hn[0]; cd[1] = hn[1]; cd[2] = hn[2]; cd[3] = hn[3]; }
         }
-        if (hhi && !(p.dbg & 2)) st_planes4(hhi, hlo, o1, hn);
+        if (hhi) st_planes4(hhi, hlo, o1, hn);
       }
     }
   }
@@ -831,7 +824,6 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
   p.bn = choose_bn(g.N);
   p.fuse = g.fuse; p.gru = g.gru;
-  { static const int dbg = getenv("LFI_DBG_GRU") ? atoi(getenv("LFI_DBG_GRU")) : 0; p.dbg = dbg; }
   if (g.fuse == LFI_FUSE_GRU_FWD) {
     LFI_REQUIRE(g.gru.E % 64 == 0 && g.N == 3 * g.gru.E && !B.mn && g.batch == 1, LFI_ERR_SHAPE, "gemm_tc: fused GRU forward needs E %% 64 == 0");
     p.bn = 192;
