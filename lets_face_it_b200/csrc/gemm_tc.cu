@@ -31,11 +31,13 @@ namespace tc {
 constexpr int BM = 128;        // tile rows (UMMA M, cta_group::1)
 constexpr int BK = 64;         // bf16 elements per k-block = one 128-byte swizzle span
 constexpr int UK = 16;         // UMMA K for 16-bit operands
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kEpiWarps = 8;       // generic epilogue; the fused GRU forward runs kGruEpiWarps (its epilogue is latency bound)
+constexpr int kGruEpiWarps = 8;   // (16 epilogue warps were measured slower: 96 registers per thread spill, 2.88 vs 2.37 ms per step)
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + epilogue warps
+__host__ __device__ constexpr int threads_for(int ew) { return 64 + 32 * ew; }
+__host__ __device__ constexpr int epi_bytes_for(int ew) { return ew * 32 * 20 * 4; }
 constexpr int kMaxStages = 8;
 constexpr int kEpiPitch = 20;  // floats; 32 rows x 16 columns per staging pass, conflict-free for 128-bit accesses
-constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch * 4;
 constexpr int kTmemCols = 512;  // two accumulator tiles of up to 256 columns
 constexpr int kSmemLimit = 225 * 1024;  // dynamic; leaves room for the 1 KB alignment reserve
 
@@ -277,7 +279,7 @@ __device__ __forceinline__ void chunk_to_rows(uint32_t taddr, float *stg, int la
 // Per 16-unit chunk: all global operands are requested first (they do not depend on the accumulator), then the
 // accumulator chunks are pulled out of TMEM, then gate math and stores.
 __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t, uint32_t tbase, float *stg, int q, int half, int lane,
-                                             uint64_t *tfull, uint32_t aph) {
+                                             uint64_t *tfull, uint32_t aph, int nsub) {
   const GruEpi &G = p.gru;
   const int E = G.E;
   const int rr = lane & 7, cg = (lane >> 3) * 4;
@@ -286,7 +288,7 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
   __nv_bfloat16 *hhi = (__nv_bfloat16 *)G.h_hi, *hlo = (__nv_bfloat16 *)G.h_lo;
   const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
   bool waited = false;
-  for (int sc = half; sc < 4; sc += 2) {
+  for (int sc = half; sc < 4; sc += nsub) {
     const int e = min(u_base + 16 * sc + cg, E - 4);
     float4 xr[4], xu[4], xn[4], hp[4];
     float mk[4];
@@ -358,7 +360,7 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
 // dh_{s-1} = tile + dh (direct part), then the gate backward of step s-1.  Bias gradients: per-lane sums over its four
 // rows, butterfly over the eight row lanes, one atomic per column and warp.
 __device__ __forceinline__ void gru_bwd_tile(const Params &p, const TileCoord &t, uint32_t tbase, float *stg, int q, int half, int lane,
-                                             uint64_t *tfull, uint32_t aph) {
+                                             uint64_t *tfull, uint32_t aph, int nsub) {
   const GruEpi &G = p.gru;
   const int E = G.E;
   const int rr = lane & 7, cg = (lane >> 3) * 4;
@@ -366,7 +368,7 @@ __device__ __forceinline__ void gru_bwd_tile(const Params &p, const TileCoord &t
   __nv_bfloat16 *dah_hi = (__nv_bfloat16 *)G.dah_hi, *dah_lo = (__nv_bfloat16 *)G.dah_lo;
   __nv_bfloat16 *dan_hi = (__nv_bfloat16 *)G.dan_hi, *dan_lo = (__nv_bfloat16 *)G.dan_lo;
   bool waited = false;
-  for (int sc = half; sc < E / 16; sc += 2) {
+  for (int sc = half; sc < E / 16; sc += nsub) {
     const int e = 16 * sc + cg;
     float4 d4[4], r4[4], u4[4], n4[4], a4[4], h4[4];
 #pragma unroll
@@ -428,8 +430,8 @@ __device__ __forceinline__ void gru_bwd_tile(const Params &p, const TileCoord &t
   if (!waited) { mbar_wait(tfull, aph); tc_fence_after(); }
 }
 
-template <int FUSE, int CL>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int FUSE, int CL, int EW = kEpiWarps>
+__global__ void __launch_bounds__(threads_for(EW), 1)
 gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -439,7 +441,7 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
   const uint32_t b_plane = (uint32_t)(p.bn / CL) * BK * 2;  // CTA pair: each CTA stages half of the B tile
   const uint32_t stage_bytes = p.nplanes * (a_plane + b_plane);
   float *epi_stage = (float *)(smem + (size_t)p.stages * stage_bytes);
-  uint64_t *bars = (uint64_t *)((uint8_t *)epi_stage + kEpiBytes);
+  uint64_t *bars = (uint64_t *)((uint8_t *)epi_stage + epi_bytes_for(EW));
   uint64_t *full = bars, *empty = bars + kMaxStages, *tfull = bars + 2 * kMaxStages, *tempty = tfull + 2;
   uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
 
@@ -451,7 +453,7 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], CL * kEpiWarps); }  // pair: the leader's collects both epilogues
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], CL * EW); }  // pair: the leader's collects both epilogues
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 1) {
     if constexpr (CL == 2) {
@@ -587,11 +589,11 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
       bool waited = false;
       if constexpr (FUSE != LFI_FUSE_NONE) {
         const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
-        if constexpr (FUSE == LFI_FUSE_GRU_FWD) gru_fwd_tile(p, t, tb, stg, q, half, lane, &tfull[as], aph);
-        else gru_bwd_tile(p, t, tb, stg, q, half, lane, &tfull[as], aph);
+        if constexpr (FUSE == LFI_FUSE_GRU_FWD) gru_fwd_tile(p, t, tb, stg, q, half, lane, &tfull[as], aph, EW / 4);
+        else gru_bwd_tile(p, t, tb, stg, q, half, lane, &tfull[as], aph, EW / 4);
         waited = true;
       }
-      for (int sc = half; sc < p.bn / 16 && FUSE == LFI_FUSE_NONE; sc += 2) {
+      for (int sc = half; sc < p.bn / 16 && FUSE == LFI_FUSE_NONE; sc += EW / 4) {
         const int nc0 = t.n0 + sc * 16;
         if (nc0 >= p.N) break;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + sc * 16;
@@ -863,7 +865,8 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   const int CL = pair ? 2 : 1;
   p.tiles_m = (g.M + BM - 1) / BM; p.tiles_n = (g.N + p.bn - 1) / p.bn;
   const int stage_bytes = nplanes * (BM * BK * 2 + (p.bn / CL) * BK * 2);  // per CTA
-  const int fixed = kEpiBytes + (2 * kMaxStages + 4) * 8 + 16 + 1024;
+  const int ew = g.fuse == LFI_FUSE_GRU_FWD ? kGruEpiWarps : kEpiWarps;
+  const int fixed = epi_bytes_for(ew) + (2 * kMaxStages + 4) * 8 + 16 + 1024;
   p.stages = (kSmemLimit - fixed) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   LFI_REQUIRE(p.stages >= 2, LFI_ERR_SHAPE, "gemm_tc: tile does not fit shared memory");
@@ -917,7 +920,7 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   if (!attr_set) {
     LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_NONE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_NONE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_GRU_FWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_GRU_FWD, 1, kGruEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_GRU_BWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
@@ -925,7 +928,7 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   const int grid = (int)(ntiles < g_sms ? ntiles : g_sms);
   // request > half of the SM's shared memory so that two CTAs (each wanting all 512 TMEM columns) never share an SM
   const int smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;
-  if (g.fuse == LFI_FUSE_GRU_FWD) gemm_tc_kernel<LFI_FUSE_GRU_FWD, 1><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
+  if (g.fuse == LFI_FUSE_GRU_FWD) gemm_tc_kernel<LFI_FUSE_GRU_FWD, 1, kGruEpiWarps><<<grid, threads_for(kGruEpiWarps), smem_req, st>>>(p, mA0, mA1, mB0, mB1);
   else if (g.fuse == LFI_FUSE_GRU_BWD) gemm_tc_kernel<LFI_FUSE_GRU_BWD, 1><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
   else if (pair) {
     // CTA pairs: one 256-row cta_group::2 tile per cluster
