@@ -13,6 +13,9 @@
 
 namespace lfi {
 
+size_t gemm_ws_bytes(int mode, const GemmArgs &g);  // gemm_dispatch.cu: operand-plane scratch one GEMM needs
+static size_t gemm_ws_bytes_for(int mode, const GemmArgs &g) { return gemm_ws_bytes(mode, g); }
+
 // ------------------------------------------------------------------------------------------------
 // derived cache layout (floats)
 struct DerivedLayout {
@@ -511,20 +514,39 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
     }
     LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
     if (!w.cp) LFI_TRY(aux::colsum(g->bc, w.dC, K * D, (int)M, K * D, 1.0f, st));
+    // d W_c = dC^T cond: not needed by the rest of the backward pass.  With the side stream available it runs there, next to the
+    // encoder backward (its operand-plane scratch sits behind the region the d cond GEMM of the main stream uses).
     GemmArgs r = gemm_args(1, 0, K * D, d.Fe, (int)M, w.dC, K * D, w.cond, d.Fe, w.dWcF, d.Fe, 0);
     if (w.cp) r.pA = plane_ref(w.dC_hi, w.dC_lo, K * D);
-    LFI_TRY(gemm_dispatch(gemm_mode, r, gws, gws_bytes, st));
-    LFI_TRY(aux::unfold_wc_grad(g->wc, w.dWcF, d, *s, st));
-  }
-  if (g_grad_ready_event) {  // data parallel: every flow-step weight gradient is final here, once the side-stream GEMMs are too
-    if (wg_par) {  // record on the side stream, ordered after this point of the main stream (no early join of the main stream)
-      static cudaEvent_t ev_unfold = nullptr;
-      if (!ev_unfold) LFI_CUDA(cudaEventCreateWithFlags(&ev_unfold, cudaEventDisableTiming));
-      LFI_CUDA(cudaEventRecord(ev_unfold, st));
-      LFI_CUDA(cudaStreamWaitEvent(wg_stream, ev_unfold, 0));
-      LFI_CUDA(cudaEventRecord(g_grad_ready_event, wg_stream));
+    size_t side_off = 0;
+    bool wc_side = false;
+    if (wg_par && env_flag("LFI_DWC_STREAM", true)) {
+      GemmArgs qd = gemm_args(0, 0, (int)M, d.Fe, K * D, nullptr, K * D, WcF, d.Fe, nullptr, d.Fe, 0);
+      side_off = round_up_sz(gemm_ws_bytes_for(gemm_mode, qd), 1024);
+      wc_side = side_off + gemm_ws_bytes_for(gemm_mode, r) <= gws_bytes;
+    }
+    if (wc_side) {
+      static cudaEvent_t ev_dc = nullptr;
+      if (!ev_dc) LFI_CUDA(cudaEventCreateWithFlags(&ev_dc, cudaEventDisableTiming));
+      LFI_CUDA(cudaEventRecord(ev_dc, st));
+      LFI_CUDA(cudaStreamWaitEvent(wg_stream, ev_dc, 0));
+      LFI_TRY(gemm_dispatch(gemm_mode, r, (char *)gws + side_off, gws_bytes - side_off, wg_stream));
+      LFI_TRY(aux::unfold_wc_grad(g->wc, w.dWcF, d, *s, wg_stream));
+      if (g_grad_ready_event) LFI_CUDA(cudaEventRecord(g_grad_ready_event, wg_stream));  // every flow-step weight gradient is final
     } else {
-      LFI_CUDA(cudaEventRecord(g_grad_ready_event, st));
+      LFI_TRY(gemm_dispatch(gemm_mode, r, gws, gws_bytes, st));
+      LFI_TRY(aux::unfold_wc_grad(g->wc, w.dWcF, d, *s, st));
+      if (g_grad_ready_event) {  // data parallel: every flow-step weight gradient is final here, once the side-stream GEMMs are too
+        if (wg_par) {  // record on the side stream, ordered after this point of the main stream (no early join of the main stream)
+          static cudaEvent_t ev_unfold = nullptr;
+          if (!ev_unfold) LFI_CUDA(cudaEventCreateWithFlags(&ev_unfold, cudaEventDisableTiming));
+          LFI_CUDA(cudaEventRecord(ev_unfold, st));
+          LFI_CUDA(cudaStreamWaitEvent(wg_stream, ev_unfold, 0));
+          LFI_CUDA(cudaEventRecord(g_grad_ready_event, wg_stream));
+        } else {
+          LFI_CUDA(cudaEventRecord(g_grad_ready_event, st));
+        }
+      }
     }
   }
   // d cond for the encoder columns only (inputs carry no gradient)
