@@ -79,6 +79,20 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_first(self, timeout=4.0):
+        """Blocks until nvidia-smi has written its first poll (it needs a few hundred ms to start: a short warm-up + timed
+        region would otherwise be over before the first sample)."""
+        if self.proc is None:
+            return
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.02)
+
     def stop(self, window=None):
         """window = (t0, t1) host epoch seconds of the timed region: only samples inside it are used (the sampler is started
         before the warm-up so that nvidia-smi is already running when the region begins)."""
@@ -267,6 +281,11 @@ def run_ours(a):
         clocks.start()
     for _ in range(max(a.warmup, 3)):
         trainer.step(dbatch)
+    if not a.ncu_step:
+        sync()
+        clocks.wait_first()      # the poller is running before the timed region starts ...
+        for _ in range(2):       # ... and the GPU is back under load when it does
+            trainer.step(dbatch)
     if a.ncu_step:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
