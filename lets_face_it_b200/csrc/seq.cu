@@ -437,6 +437,9 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   const DerivedLayout L = derived_layout(d);
   const float *WcF = (const float *)derived + L.WcF;
 
+  // Numerics of the time-parallel backward GEMMs: the mode of the call, or (LFI_BWD_BF16=1, an option measured next to the
+  // parity mode, not its default) single bf16 products on the hi planes while the forward pass and the flow core keep split-bf16
+  const int bmode = (gemm_mode == LFI_GEMM_BF16X3 && env_flag("LFI_BWD_BF16", false)) ? LFI_GEMM_BF16 : gemm_mode;
   // 1. sequential core, reverse wavefronts
   core::BwdArgs a;
   memset(&a, 0, sizeof(a));
@@ -480,7 +483,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
     GemmArgs q = gemm_args(1, 0, Mo, No, (int)red, A, lda, Bm, ldb, Cm, ldc, LFI_EPI_ACCUM);
     q.batch = K; q.sA = sA; q.sB = sB; q.sC = sC;
     if (w.cp) { q.pA = pa; q.pB = pb; }
-    return gemm_dispatch(gemm_mode, q, gws, gws_bytes, st);
+    return gemm_dispatch(bmode, q, gws, gws_bytes, st);
   };
   const PlaneRef pdG = plane_ref(w.dG_hi, w.dG_lo, K * GH, GH), ph = plane_ref(w.h_hi, w.h_lo, H, (long)(M * H));
   if (Tp > 1)  // dW_hh[k] += dA_h[k][t>=1]^T h[k][t-1]
@@ -512,7 +515,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
       q.aux = nullptr; q.auxp = w.cact_hi; q.ldauxp = K * D; q.sAuxp = D;
       q.colsum = g->bc; q.sColsum = D;
     }
-    LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
+    LFI_TRY(gemm_dispatch(bmode, q, gws, gws_bytes, st));
     if (!w.cp) LFI_TRY(aux::colsum(g->bc, w.dC, K * D, (int)M, K * D, 1.0f, st));
     // d W_c = dC^T cond: not needed by the rest of the backward pass.  With the side stream available it runs there, next to the
     // encoder backward (its operand-plane scratch sits behind the region the d cond GEMM of the main stream uses).
@@ -530,11 +533,11 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
       if (!ev_dc) LFI_CUDA(cudaEventCreateWithFlags(&ev_dc, cudaEventDisableTiming));
       LFI_CUDA(cudaEventRecord(ev_dc, st));
       LFI_CUDA(cudaStreamWaitEvent(wg_stream, ev_dc, 0));
-      LFI_TRY(gemm_dispatch(gemm_mode, r, (char *)gws + side_off, gws_bytes - side_off, wg_stream));
+      LFI_TRY(gemm_dispatch(bmode, r, (char *)gws + side_off, gws_bytes - side_off, wg_stream));
       LFI_TRY(aux::unfold_wc_grad(g->wc, w.dWcF, d, *s, wg_stream));
       if (g_grad_ready_event) LFI_CUDA(cudaEventRecord(g_grad_ready_event, wg_stream));  // every flow-step weight gradient is final
     } else {
-      LFI_TRY(gemm_dispatch(gemm_mode, r, gws, gws_bytes, st));
+      LFI_TRY(gemm_dispatch(bmode, r, gws, gws_bytes, st));
       LFI_TRY(aux::unfold_wc_grad(g->wc, w.dWcF, d, *s, st));
       if (g_grad_ready_event) {  // data parallel: every flow-step weight gradient is final here, once the side-stream GEMMs are too
         if (wg_par) {  // record on the side stream, ordered after this point of the main stream (no early join of the main stream)
@@ -557,7 +560,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   {
     GemmArgs q = gemm_args(0, 0, (int)M, d.Fe - enc_lo, K * D, w.dC, K * D, WcF + enc_lo, d.Fe, w.dcond + enc_lo, d.Fe, 0);
     if (w.cp) q.pA = plane_ref(w.dC_hi, w.dC_lo, K * D);
-    LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
+    LFI_TRY(gemm_dispatch(bmode, q, gws, gws_bytes, st));
   }
 
   // 4. encoder GRUs, BPTT over the window (models.py:63-64).  Per step only the gate math and dh_prev = dA_h W_hh
@@ -602,22 +605,22 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
           q.dan_hi = off16(ew.dan_hi, (size_t)(sidx - 1) * M * E);     q.dan_lo = lo ? off16(ew.dan_lo, (size_t)(sidx - 1) * M * E) : nullptr;
           q.gb_ih = g->enc_b_ih[m]; q.gb_hh = g->enc_b_hh[m];
         }
-        LFI_TRY(gemm_dispatch(gemm_mode, t, gws, gws_bytes, st));
+        LFI_TRY(gemm_dispatch(bmode, t, gws, gws_bytes, st));
       }
     }
     const int Kall = (int)(hist * M), Khh = (int)((hist - 1) * M);
     if (hist > 1) {  // dW_hh += sum_{s>=1} dA_h[s]^T h[s-1]
       GemmArgs q = gemm_args(1, 0, 3 * E, E, Khh, ew.dah32 ? ew.dah32 + M * 3 * E : nullptr, 3 * E, ew.hs, E, g->enc_w_hh[m], E, LFI_EPI_ACCUM);
       if (ew.planes) { q.pA = plane_ref(off16(ew.dah_hi, M * 3 * E), lo ? off16(ew.dah_lo, M * 3 * E) : nullptr, 3 * E); q.pB = plane_ref(ew.hp_hi, ew.hp_lo, E); }
-      LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
+      LFI_TRY(gemm_dispatch(bmode, q, gws, gws_bytes, st));
     }
     {  // dW_ih rows [0,2E) += dA_h[:, :2E]^T x  (r, u blocks coincide with the i-side gradients); rows [2E,3E) += dA_n^T x
       GemmArgs q = gemm_args(1, 0, 2 * E, dim, Kall, ew.dah32, 3 * E, ew.xg32, dim, g->enc_w_ih[m], dim, LFI_EPI_ACCUM);
       if (ew.planes) { q.pA = plane_ref(ew.dah_hi, ew.dah_lo, 3 * E); q.pB = plane_ref(ew.xg_hi, ew.xg_lo, dimp); }
-      LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
+      LFI_TRY(gemm_dispatch(bmode, q, gws, gws_bytes, st));
       GemmArgs r = gemm_args(1, 0, E, dim, Kall, ew.dan32, E, ew.xg32, dim, g->enc_w_ih[m] + (size_t)2 * E * dim, dim, LFI_EPI_ACCUM);
       if (ew.planes) { r.pA = plane_ref(ew.dan_hi, ew.dan_lo, E); r.pB = plane_ref(ew.xg_hi, ew.xg_lo, dimp); }
-      LFI_TRY(gemm_dispatch(gemm_mode, r, gws, gws_bytes, st));
+      LFI_TRY(gemm_dispatch(bmode, r, gws, gws_bytes, st));
     }
     return LFI_OK;
   };
