@@ -9,8 +9,10 @@
 // M = 128 accumulator lanes: every product is issued twice, once on the A operand as stored (sequences in lanes 0..63)
 // against the weight rows of hidden units 0..31, once with the A descriptor moved back by 64 rows (the same sequences
 // land in lanes 64..127) against the rows of units 32..63 - all 128 lanes, i.e. all eight warps, then hold useful
-// accumulators (thread = sequence x 16 hidden units).  Operands: a = a_hi + a_lo, three products a_hi b_hi + a_hi b_lo + a_lo b_hi, fp32-grade (same numerics as the bf16x3
-// GEMMs of the time-parallel phase).  The weights are split once per launch into resident hi / lo planes in the canonical
+// accumulators (thread = sequence x 16 hidden units).  Operands: a = a_hi + a_lo, three products a_hi b_hi + a_hi b_lo +
+// a_lo b_hi, fp32-grade (same numerics as the bf16x3 GEMMs of the time-parallel phase).  A ninth warp issues every MMA, so
+// that the issue latency of the frame's ~100 instructions never holds up the eight compute warps (they synchronise among
+// themselves with a named barrier and with the issuer through bar.arrive / bar.sync and mbarrier commits).  The weights are split once per launch into resident hi / lo planes in the canonical
 // K-major swizzled UMMA layout; the state h and z1 are written as hi / lo planes by the threads that produce them (own
 // half locally, the other CTA's copy through distributed shared memory).  Gate math reads the accumulators with
 // tcgen05.ld (thread = sequence) - reference: nn.GRUCell inside f_seq.forward, models.py:204-214; LinearZeros

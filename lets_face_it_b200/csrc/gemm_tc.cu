@@ -14,8 +14,10 @@
 //   warp 0   : TMA producer   - cp.async.bulk.tensor (128B swizzle) of the A / B planes into a ring of stages
 //   warp 1   : MMA issuer     - one thread issues tcgen05.mma (M=128, N=bn<=256, K=16) into one of two TMEM
 //                               accumulator tiles and commits stage / accumulator barriers
-//   warps 2-5: epilogue       - tcgen05.ld the finished accumulator, transpose through shared memory, fused
+//   warps 2-9: epilogue       - tcgen05.ld the finished accumulator, transpose through shared memory, fused
 //                               epilogue, fully coalesced global stores (or red.add for split-K)
+// Large GEMMs run as CTA pairs (2-CTA clusters, tcgen05.mma.cta_group::2): one MMA covers a 256-row tile, each CTA
+// stages its 128 rows of A and half of the B tile, the leader CTA issues, completion is committed to both CTAs.
 // Both operand majors are native: a row-major [MN, K] plane is a K-major UMMA operand, a row-major [K, MN]
 // plane (weight-gradient GEMMs reduce over the rows of two activation matrices) is an MN-major operand, so no
 // transposed copies of activations are ever materialised.
