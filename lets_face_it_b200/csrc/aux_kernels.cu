@@ -177,6 +177,45 @@ int gather_windows(float *dst, int ld, int layout_steps, const float *x, const f
 }
 
 // ------------------------------------------------------------------------------------------------
+// thread = 8 consecutive input features of one (window step, window): 16-byte stores into each plane
+__global__ void gather_windows_planes_kernel(__nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int ldp, const float *__restrict__ x,
+                                             const float *__restrict__ mask, int B, int T, int dim, int hist, int off, int t0, int Tp) {
+  const size_t M = (size_t)Tp * B;
+  const int groups = ldp >> 3;
+  const size_t n = M * hist * groups;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(e % groups) * 8;
+    const size_t q = e / groups;
+    const size_t m = q % M;
+    const int s = (int)(q / M);
+    const int b = (int)(m % B), tp = (int)(m / B);
+    const int tau = t0 + tp - hist + off + s;
+    const float *src = x + ((size_t)b * T + tau) * dim + c0;
+    const float mk = mask ? mask[m * hist + s] : 1.0f;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c0 + j < dim) ? src[j] * mk : 0.f;
+    __align__(16) __nv_bfloat16 h8[8], l8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h8[j] = __float2bfloat16_rn(v[j]);
+      l8[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h8[j]));
+    }
+    const size_t o = ((size_t)s * M + m) * ldp + c0;
+    *reinterpret_cast<uint4 *>(hi + o) = *reinterpret_cast<const uint4 *>(h8);
+    if (lo) *reinterpret_cast<uint4 *>(lo + o) = *reinterpret_cast<const uint4 *>(l8);
+  }
+}
+int gather_windows_planes(void *hi, void *lo, int ldp, const float *x, const float *mask, int B, int T, int dim, int hist, int off, int t0,
+                          int Tp, cudaStream_t st) {
+  LFI_REQUIRE(ldp % 8 == 0 && ldp >= dim && (((uintptr_t)hi | (uintptr_t)lo) & 15) == 0, LFI_ERR_ARG, "gather_windows_planes: plane pitch / alignment");
+  gather_windows_planes_kernel<<<blocks_for((size_t)Tp * B * hist * (ldp / 8)), TB, 0, st>>>((__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, ldp, x, mask, B,
+                                                                                             T, dim, hist, off, t0, Tp);
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void enc_gate_fwd_kernel(EncStep a) {
   const size_t M = (size_t)a.Tp * a.B;
   const int E = a.E;

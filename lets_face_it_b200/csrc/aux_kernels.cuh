@@ -83,6 +83,10 @@ int clip_adam(float *theta, const float *grad, float *m, float *v, size_t n, flo
 
 int fill(float *p, float v, size_t n, cudaStream_t st);
 
+// masked window inputs straight into split-bf16 operand planes [hist][M][ldp] (ldp = round_up(dim, 8), padding zero): the
+// gather_windows(layout_steps = 1) + split_to_planes pair in one pass (encoder weight-gradient operand)
+int gather_windows_planes(void *hi, void *lo, int ldp, const float *x, const float *mask, int B, int T, int dim, int hist, int off, int t0,
+                          int Tp, cudaStream_t st);
 // out1[b*so + j] (+ out2[..] where (j % period) < lim2) += sum over rows of (hi + lo)[b][r][col0 + j]: column sums of split-bf16 planes
 int colsum_planes(float *out1, float *out2, int period, int lim2, long so, const void *hi, const void *lo, int ld, long sb, int batch, int rows,
                   int col0, int cols, cudaStream_t st);

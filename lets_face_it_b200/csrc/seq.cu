@@ -573,8 +573,10 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
     EncWs &ew = w.enc[m];
     const bool lo = gemm_mode == LFI_GEMM_BF16X3;
     const int dimp = round_up(dim, 8);
-    LFI_TRY(aux::gather_windows(ew.xg32, dim, 1, bt->x[m], bt->mask[m], B, T, dim, hist, 1, d.start_ts, Tp, st));
-    if (ew.planes) LFI_TRY(split_to_planes(ew.xg32, (int)(hist * M), dim, dim, 0, 1, ew.xg_hi, lo ? ew.xg_lo : nullptr, st));
+    if (ew.planes)  // masked window inputs straight into the operand planes of the dW_ih GEMMs
+      LFI_TRY(aux::gather_windows_planes(ew.xg_hi, lo ? ew.xg_lo : nullptr, dimp, bt->x[m], bt->mask[m], B, T, dim, hist, 1, d.start_ts, Tp, st));
+    else
+      LFI_TRY(aux::gather_windows(ew.xg32, dim, 1, bt->x[m], bt->mask[m], B, T, dim, hist, 1, d.start_ts, Tp, st));
     LFI_TRY(aux::fill(ew.dhe, 0.f, M * E, st));
     const bool fused = ew.planes && (E == 64 || E == 128 || E == 192 || E == 256) && env_flag("LFI_FUSED_GRU_BWD", false);
     for (int sidx = hist - 1; sidx >= 0; --sidx) {
