@@ -285,12 +285,13 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
   const GruEpi &G = p.gru;
   const int E = G.E;
   const int rr = lane & 7, cg = (lane >> 3) * 4;
-  const int u_base = (t.n0 / 192) * 64;
+  const int UT = p.bn / 3;  // hidden units per tile (64 or 32): TMEM columns [0,UT) r, [UT,2UT) u, [2UT,3UT) n
+  const int u_base = (t.n0 / p.bn) * UT;
   const int mrow0 = t.m0 + q * 32;
   __nv_bfloat16 *hhi = (__nv_bfloat16 *)G.h_hi, *hlo = (__nv_bfloat16 *)G.h_lo;
   const uint64_t pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
   bool waited = false;
-  for (int sc = half; sc < 4; sc += nsub) {
+  for (int sc = half; sc < UT / 16; sc += nsub) {
     const int e = min(u_base + 16 * sc + cg, E - 4);
     float4 xr[4], xu[4], xn[4], hp[4];
     float mk[4];
@@ -311,8 +312,8 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
     if (!waited) { mbar_wait(tfull, aph); tc_fence_after(); waited = true; }
     float ar[4][4], au[4][4], an[4][4];
     chunk_to_rows(tbase + sc * 16, stg, lane, rr, cg, ar);
-    chunk_to_rows(tbase + 64 + sc * 16, stg, lane, rr, cg, au);
-    chunk_to_rows(tbase + 128 + sc * 16, stg, lane, rr, cg, an);
+    chunk_to_rows(tbase + UT + sc * 16, stg, lane, rr, cg, au);
+    chunk_to_rows(tbase + 2 * UT + sc * 16, stg, lane, rr, cg, an);
     if (u_base + 16 * sc + cg >= E) continue;
     const float bir_[4] = {bir.x, bir.y, bir.z, bir.w}, biu_[4] = {biu.x, biu.y, biu.z, biu.w}, bin_[4] = {bin.x, bin.y, bin.z, bin.w};
     const float bhr_[4] = {bhr.x, bhr.y, bhr.z, bhr.w}, bhu_[4] = {bhu.x, bhu.y, bhu.z, bhu.w}, bhn_[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
@@ -501,8 +502,8 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
             }
             if (FUSE == LFI_FUSE_GRU_FWD) {
               // 64 hidden units x (r, u, n): three 64-row boxes of W_hh, 8-row swizzle atoms stay contiguous
-              const int u0 = (t.n0 / 192) * 64;
-              for (int g = 0; g < 3; ++g) tma_load_3d(sb + pl * b_plane + g * (64 * 128), mb, &full[s], k0, g * p.gru.E + u0, t.b);
+              const int ut = p.bn / 3, u0 = (t.n0 / p.bn) * ut;  // (ut rows per gate box)
+              for (int g = 0; g < 3; ++g) tma_load_3d(sb + pl * b_plane + g * (ut * 128), mb, &full[s], k0, g * p.gru.E + u0, t.b);
             } else if constexpr (CL == 2) {
               // this CTA stages its half of the B tile: columns [n0 + rank * bn/2, + bn/2)
               const int half = p.bn / 2;
@@ -830,7 +831,9 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   p.fuse = g.fuse; p.gru = g.gru;
   if (g.fuse == LFI_FUSE_GRU_FWD) {
     LFI_REQUIRE(g.gru.E % 64 == 0 && g.N == 3 * g.gru.E && !B.mn && g.batch == 1, LFI_ERR_SHAPE, "gemm_tc: fused GRU forward needs E %% 64 == 0");
-    p.bn = 192;
+    // 64 hidden units per tile, or 32 (LFI_GRU_TILE32=1): twice the tiles, half the epilogue per tile, a finer last wave
+    static const bool tile32 = env_flag("LFI_GRU_TILE32", false);
+    p.bn = tile32 ? 96 : 192;
     const float *cd = g.gru.cond;
     p.cond_vec = cd && (((uintptr_t)cd & 15) == 0) && g.gru.cond_ld % 4 == 0;
   } else if (g.fuse == LFI_FUSE_GRU_BWD) {
@@ -908,7 +911,7 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   if (g.pOut.hi) p.vec = p.vec && al16(g.pOut.hi) && (!g.pOut.lo || al16(g.pOut.lo)) && g.pOut.ld % 4 == 0 && g.pOut.stride % 4 == 0;
 
   CUtensorMap mA0, mA1, mB0, mB1;
-  const int a_box = A.mn ? BK : BM, b_box = B.mn ? BK : (g.fuse == LFI_FUSE_GRU_FWD ? 64 : (pair ? p.bn / 2 : p.bn));
+  const int a_box = A.mn ? BK : BM, b_box = B.mn ? BK : (g.fuse == LFI_FUSE_GRU_FWD ? p.bn / 3 : (pair ? p.bn / 2 : p.bn));
   LFI_TRY(make_map(&mA0, A.hi, A.rows, A.cols, A.ldp, A.stride, g.batch, a_box));
   LFI_TRY(make_map(&mB0, B.hi, B.rows, B.cols, B.ldp, B.stride, g.batch, b_box));
   if (nplanes == 2) {
