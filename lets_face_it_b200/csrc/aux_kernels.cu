@@ -526,13 +526,23 @@ __global__ void clip_adam_kernel(float *theta, const float *grad, float *m, floa
   if (max_norm > 0.f) coef = fminf(max_norm / (norm + 1e-6f), 1.0f);
   const float gs = grad_scale * coef;
   const float step = lr / bc1;
-  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-    const float g = grad[e] * gs;
-    const float mm = b1 * m[e] + omb1 * g;
-    const float vv = b2 * v[e] + omb2 * g * g;
-    m[e] = mm; v[e] = vv;
-    theta[e] -= step * mm / (sqrtf(vv) / bc2_sqrt + eps);
+  auto upd = [&](float &th, float gr, float &mo, float &ve) {
+    const float g = gr * gs;
+    const float mm = b1 * mo + omb1 * g;
+    const float vv = b2 * ve + omb2 * g * g;
+    mo = mm; ve = vv;
+    th -= step * mm / (sqrtf(vv) / bc2_sqrt + eps);
+  };
+  const bool vec = ((((uintptr_t)theta | (uintptr_t)grad | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  const size_t n4 = vec ? n / 4 : 0;  // 128-bit accesses over the aligned body (four streams in, three out: HBM bound)
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
+    float4 t4 = reinterpret_cast<float4 *>(theta)[e], m4 = reinterpret_cast<float4 *>(m)[e], v4 = reinterpret_cast<float4 *>(v)[e];
+    const float4 g4 = reinterpret_cast<const float4 *>(grad)[e];
+    upd(t4.x, g4.x, m4.x, v4.x); upd(t4.y, g4.y, m4.y, v4.y); upd(t4.z, g4.z, m4.z, v4.z); upd(t4.w, g4.w, m4.w, v4.w);
+    reinterpret_cast<float4 *>(theta)[e] = t4; reinterpret_cast<float4 *>(m)[e] = m4; reinterpret_cast<float4 *>(v)[e] = v4;
   }
+  for (size_t e = 4 * n4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+    upd(theta[e], grad[e], m[e], v[e]);
 }
 int clip_adam(float *theta, const float *grad, float *m, float *v, size_t n, float lr, float b1, float b2, float eps,
               float max_norm, float grad_scale, int step, const float *sumsq_in, cudaStream_t st) {
@@ -540,7 +550,7 @@ int clip_adam(float *theta, const float *grad, float *m, float *v, size_t n, flo
   const double b1d = (double)b1, b2d = (double)b2;
   const float bc1 = (float)(1.0 - pow(b1d, (double)step));
   const float bc2s = (float)sqrt(1.0 - pow(b2d, (double)step));
-  clip_adam_kernel<<<blocks_for(n, TB, 148 * 8), TB, 0, st>>>(theta, grad, m, v, n, lr, b1, b2, (float)(1.0 - b1d),
+  clip_adam_kernel<<<blocks_for((n + 3) / 4, TB, 148 * 8), TB, 0, st>>>(theta, grad, m, v, n, lr, b1, b2, (float)(1.0 - b1d),
                                                                (float)(1.0 - b2d), eps, max_norm, grad_scale, bc1, bc2s,
                                                                sumsq_in);
   LFI_LAUNCH_CHECK();
