@@ -252,7 +252,78 @@ __global__ void enc_gate_fwd_kernel(EncStep a) {
     }
   }
 }
+// Vectorised variant (E % 4 == 0, 16-byte aligned streams): thread = 4 consecutive hidden units of one window
+__global__ void enc_gate_fwd_v4_kernel(EncStep a) {
+  const size_t M = (size_t)a.Tp * a.B;
+  const int E = a.E, E4 = E >> 2;
+  const size_t n = M * E4;
+  for (size_t i4 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i4 < n; i4 += (size_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i4 % E4) * 4;
+    const size_t m = i4 / E4;
+    const size_t idx = m * E + e;
+    const int b = (int)(m % a.B), tp = (int)(m / a.B);
+    const int tau = a.t0 + tp - a.hist + 1 + a.s;
+    const float mk = a.mask ? a.mask[m * a.hist + a.s] : 1.0f;
+    const float *xp = a.xp + ((size_t)b * a.T + tau) * 3 * E + e;
+    const float4 xr = *reinterpret_cast<const float4 *>(xp), xu = *reinterpret_cast<const float4 *>(xp + E), xn = *reinterpret_cast<const float4 *>(xp + 2 * E);
+    const float4 bir = *reinterpret_cast<const float4 *>(a.b_ih + e), biu = *reinterpret_cast<const float4 *>(a.b_ih + E + e),
+                 bin = *reinterpret_cast<const float4 *>(a.b_ih + 2 * E + e);
+    float4 ahr = *reinterpret_cast<const float4 *>(a.b_hh + e), ahu = *reinterpret_cast<const float4 *>(a.b_hh + E + e),
+           ahn = *reinterpret_cast<const float4 *>(a.b_hh + 2 * E + e);
+    if (a.gh) {
+      const float *g = a.gh + m * 3 * E + e;
+      const float4 gr = *reinterpret_cast<const float4 *>(g), gu = *reinterpret_cast<const float4 *>(g + E), gn = *reinterpret_cast<const float4 *>(g + 2 * E);
+      ahr.x += gr.x; ahr.y += gr.y; ahr.z += gr.z; ahr.w += gr.w;
+      ahu.x += gu.x; ahu.y += gu.y; ahu.z += gu.z; ahu.w += gu.w;
+      ahn.x += gn.x; ahn.y += gn.y; ahn.z += gn.z; ahn.w += gn.w;
+    }
+    const float4 hp = a.hprev ? *reinterpret_cast<const float4 *>(a.hprev + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float xr_[4] = {xr.x, xr.y, xr.z, xr.w}, xu_[4] = {xu.x, xu.y, xu.z, xu.w}, xn_[4] = {xn.x, xn.y, xn.z, xn.w};
+    const float bir_[4] = {bir.x, bir.y, bir.z, bir.w}, biu_[4] = {biu.x, biu.y, biu.z, biu.w}, bin_[4] = {bin.x, bin.y, bin.z, bin.w};
+    const float ahr_[4] = {ahr.x, ahr.y, ahr.z, ahr.w}, ahu_[4] = {ahu.x, ahu.y, ahu.z, ahu.w}, ahn_[4] = {ahn.x, ahn.y, ahn.z, ahn.w};
+    const float hp_[4] = {hp.x, hp.y, hp.z, hp.w};
+    float rg[4], ug[4], ng[4], h[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // same arithmetic as the scalar kernel
+      rg[c] = sigmoidf_(mk * xr_[c] + bir_[c] + ahr_[c]);
+      ug[c] = sigmoidf_(mk * xu_[c] + biu_[c] + ahu_[c]);
+      ng[c] = tanhf(mk * xn_[c] + bin_[c] + rg[c] * ahn_[c]);
+      h[c] = ng[c] + ug[c] * (hp_[c] - ng[c]);
+    }
+    *reinterpret_cast<float4 *>(a.h + idx) = make_float4(h[0], h[1], h[2], h[3]);
+    if (a.gates && a.gates16) {
+      unsigned short *g = reinterpret_cast<unsigned short *>(a.gates) + m * 3 * E + e;
+      *reinterpret_cast<uint2 *>(g) = make_uint2(q_unorm16(rg[0]) | ((unsigned)q_unorm16(rg[1]) << 16), q_unorm16(rg[2]) | ((unsigned)q_unorm16(rg[3]) << 16));
+      *reinterpret_cast<uint2 *>(g + E) = make_uint2(q_unorm16(ug[0]) | ((unsigned)q_unorm16(ug[1]) << 16), q_unorm16(ug[2]) | ((unsigned)q_unorm16(ug[3]) << 16));
+      *reinterpret_cast<uint2 *>(g + 2 * E) = make_uint2(q_snorm16(ng[0]) | ((unsigned)q_snorm16(ng[1]) << 16), q_snorm16(ng[2]) | ((unsigned)q_snorm16(ng[3]) << 16));
+    } else if (a.gates) {
+      float *g = a.gates + m * 3 * E + e;
+      *reinterpret_cast<float4 *>(g) = make_float4(rg[0], rg[1], rg[2], rg[3]);
+      *reinterpret_cast<float4 *>(g + E) = make_float4(ug[0], ug[1], ug[2], ug[3]);
+      *reinterpret_cast<float4 *>(g + 2 * E) = make_float4(ng[0], ng[1], ng[2], ng[3]);
+    }
+    if (a.ahn) *reinterpret_cast<float4 *>(a.ahn + idx) = ahn;
+    if (a.cond) {
+      float *cd = a.cond + m * a.cond_ld + e;
+      cd[0] = h[0]; cd[1] = h[1]; cd[2] = h[2]; cd[3] = h[3];
+    }
+    if (a.h_hi) {
+      __align__(8) __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { h4[c] = __float2bfloat16_rn(h[c]); l4[c] = __float2bfloat16_rn(h[c] - __bfloat162float(h4[c])); }
+      *reinterpret_cast<uint2 *>((__nv_bfloat16 *)a.h_hi + idx) = *reinterpret_cast<const uint2 *>(h4);
+      if (a.h_lo) *reinterpret_cast<uint2 *>((__nv_bfloat16 *)a.h_lo + idx) = *reinterpret_cast<const uint2 *>(l4);
+    }
+  }
+}
 int enc_gate_fwd(const EncStep &a, cudaStream_t st) {
+  auto al16 = [](const void *p) { return p == nullptr || ((uintptr_t)p & 15) == 0; };
+  if (a.E % 4 == 0 && al16(a.xp) && al16(a.gh) && al16(a.b_ih) && al16(a.b_hh) && al16(a.hprev) && al16(a.h) && al16(a.gates) && al16(a.ahn) &&
+      (((uintptr_t)a.h_hi | (uintptr_t)a.h_lo) & 7) == 0) {
+    enc_gate_fwd_v4_kernel<<<blocks_for((size_t)a.Tp * a.B * (a.E / 4)), TB, 0, st>>>(a);
+    LFI_LAUNCH_CHECK();
+    return LFI_OK;
+  }
   enc_gate_fwd_kernel<<<blocks_for((size_t)a.Tp * a.B * a.E), TB, 0, st>>>(a);
   LFI_LAUNCH_CHECK();
   return LFI_OK;
