@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--sample-frames", type=int, default=750, help="generated frames per sequence (30 s at 25 fps)")
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-batch", type=int, default=32, help="sequences per step of the CPU reference arm (bounded sample)")
+    ap.add_argument("--ref-batch", type=int, default=256, help="sequences per step of the CPU reference arm (default: the same B=256 step as our arm)")
     ap.add_argument("--no-sample", action="store_true")
     ap.add_argument("--no-bf16", action="store_true", help="skip the secondary bf16-mode timing")
     ap.add_argument("--variant", default="final", choices=["final", "wide-lstm", "wide-gru"],
@@ -205,8 +205,9 @@ def run_reference(a):
         "impl": "reference", "metric": "train frames/sec", "value": v, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "final_model.yaml training step (fwd+NLL+bwd+clip20+Adam), T=80, 56 trained frames/seq; CPU arm runs "
-                               "a bounded sample of %d sequences per step" % Bs},
+        "config": {"workload": "final_model.yaml training step (fwd+NLL+bwd+clip20+Adam), B=%d sequences, T=80 (56 trained "
+                               "frames/seq), frame dropout on; CPU arm (oracle port of the reference, all host threads)" % Bs,
+                   "global_batch": Bs},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -253,8 +254,8 @@ def run_ours(a):
     trainer = Trainer(model)
     host = make_batch(hy, B, T, seed=1 + rank, pin=True)
     dbatch = {k: v.to(dev) for k, v in host.items()}
-    trainer.step(dbatch)                  # ActNorm data-dependent init + first step (untimed)
-    trainer.broadcast_parameters(0)
+    trainer.broadcast_parameters(0)       # replicas start identical ...
+    trainer.step(dbatch)                  # ... ActNorm data-dependent init (rank 0's, broadcast inside step) + first step (untimed)
     L = cabi.lib()
 
     def sync():
@@ -430,12 +431,12 @@ def run_ours(a):
 
         # ---- CPU baseline: the oracle port on the host cores, bounded sample -------------------------------------
         if world == 1 and not a.no_cpu_baseline:
-            Bc = 32
+            Bc = B  # the same step as the GPU arm (B=256: ~10 s per step on 16 cores): one warm-up, then 2-3 steps
             step, frames = cpu_reference_step_fn(hp, Bc, T)
             step()
             t0 = time.perf_counter()
             n = 0
-            while n < 2 or (time.perf_counter() - t0 < 12 and n < 8):
+            while n < 2 or (time.perf_counter() - t0 < 20 and n < 4):
                 step()
                 n += 1
             dt = time.perf_counter() - t0

@@ -14,6 +14,7 @@
 // evaluated BEFORE the stage waits for its input: only the small products sit on the stage-to-stage critical path.
 #pragma once
 #include "core_api.cuh"
+#include <cstdio>
 #include <cuda_bf16.h>
 
 namespace lfi {
@@ -75,6 +76,46 @@ __host__ __device__ inline size_t stash_tiled_off(size_t cell, int ntiles, int t
 
 // Row-interleaved gate-ih pre-activations G (written by the gate-ih GEMM epilogue, GemmArgs::c_tiled32): element (m, n)
 __host__ __device__ inline size_t g_tiled_off(size_t m, size_t n, size_t ld) { return ((m >> 5) * (ld >> 2) + (n >> 2)) * 128 + (m & 31) * 4 + (n & 3); }
+
+// Bounded spin on a stage-progress counter (release/acquire chain between the stages of a pipeline): waits until *flag > it.
+// The chain assumes that every CTA of the launch is resident at the same time (checked on the host before the launch,
+// pipe_check_residency); if that ever fails (another context holding SMs, a protocol bug) the wait traps after 4 s and the
+// launch returns an error instead of hanging the GPU - the same policy as the mbarrier waits (tc_ptx.cuh: mbar_wait).
+__device__ __forceinline__ void spin_wait_gt(const int *flag, int it) {
+  auto ld = [&]() { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory"); return v; };
+  if (ld() > it) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (ld() <= it) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 4000000000ull) {
+      printf("lfi flow core: stage flag wait timed out (block %d,%d,%d thread %d, it %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, it);
+      __trap();
+    }
+  }
+}
+
+// Host check before a stage-pipeline launch: all `clusters` 2-CTA clusters must be co-resident (the stages spin on each other).
+// cudaOccupancyMaxActiveClusters accounts for the kernel's registers / shared memory on the current device.
+template <typename Kern>
+inline int pipe_check_residency(Kern kern, int threads, int smem_bytes, int clusters, const char *what) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2, (unsigned)clusters, 1);
+  cfg.blockDim = dim3((unsigned)threads, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {  // query unavailable: the bounded spins still protect the GPU
+    cudaGetLastError();
+    return LFI_OK;
+  }
+  LFI_REQUIRE(n >= clusters, LFI_ERR_SHAPE, "%s: %d co-resident clusters needed, the device can hold %d", what, clusters, n);
+  return LFI_OK;
+}
 
 bool pipe_supported(const Dims &d, int nk, bool bwd);
 int pipe_bwd_smem_bytes(const Dims &d);

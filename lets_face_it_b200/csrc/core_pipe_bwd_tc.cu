@@ -26,11 +26,6 @@ using namespace tcp;
 
 namespace {
 
-__device__ __forceinline__ int ld_acquire_gpu_bt(const int *p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void st_release_gpu_bt(int *p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
@@ -288,7 +283,7 @@ core_bwd_pipe_tc(const BwdArgs a, const int P, const int ntiles, int *progress) 
       // ---- 1. wait for stage k+1 ---------------------------------------------------------------------------------------
       if (!lastk) {
         if (tid == 0) {
-          while (ld_acquire_gpu_bt(wait_flag) <= it) { }
+          spin_wait_gt(wait_flag, it);
         }
         csync();
       }
@@ -625,6 +620,7 @@ int launch_bwd_pipe_tc(const BwdArgs &a, cudaStream_t st) {
   LFI_CUDA(cudaFuncSetAttribute(core_bwd_pipe_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   LFI_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)P * (K + 1) * 2 * sizeof(int), st));
   dim3 grid(2, K, P);
+  LFI_TRY(pipe_check_residency(core_bwd_pipe_tc, BNT, bytes, (int)(grid.y * grid.z), "core_bwd_pipe_tc"));
   core_bwd_pipe_tc<<<grid, BNT, bytes, st>>>(a, P, ntiles, a.flags);
   LFI_LAUNCH_CHECK();
   return LFI_OK;

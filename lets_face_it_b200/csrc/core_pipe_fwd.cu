@@ -136,7 +136,7 @@ core_fwd_pipe(const FwdArgs a, const int P, const int ntiles, int *progress) {
       // ---- 1. wait for stage k-1, ActNorm (modules.py:45-66) on this CTA's 32 rows ---------------------------------
       if (!have_x) {
         if (tid == 0) {
-          while (ld_acquire_gpu(wait_flag) <= it) { }
+          spin_wait_gt(wait_flag, it);
         }
         __syncthreads();
         fetch_x();
@@ -376,6 +376,7 @@ int launch_fwd_pipe(const FwdArgs &a, cudaStream_t st) {
   LFI_CUDA(cudaFuncSetAttribute(core_fwd_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   LFI_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)P * nk * 2 * sizeof(int), st));
   dim3 grid(2, nk, P);
+  LFI_TRY(pipe_check_residency(core_fwd_pipe, PNT, bytes, (int)(grid.y * grid.z), "core_fwd_pipe"));
   core_fwd_pipe<<<grid, PNT, bytes, st>>>(a, P, ntiles, a.flags);
   LFI_LAUNCH_CHECK();
   return LFI_OK;

@@ -300,7 +300,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
       // ---- 1. wait for stage k-1, ActNorm (modules.py:45-66) on this CTA's 32 rows ---------------------------------
       if (!have_x) {
         if (tid == 0) {
-          while (ld_acquire_gpu_t(wait_flag) <= it) { }
+          spin_wait_gt(wait_flag, it);
         }
         csync();
         fetch_x();
@@ -592,6 +592,7 @@ int launch_fwd_pipe_tc(const FwdArgs &a, cudaStream_t st) {
   static const int timing = getenv("LFI_CORE_TIMING") ? atoi(getenv("LFI_CORE_TIMING")) : 0;
   if (timing) cudaMemcpyToSymbolAsync(g_core_timing, &timing, sizeof(int), 0, cudaMemcpyHostToDevice, st);
   dim3 grid(2, nk, P);
+  LFI_TRY(pipe_check_residency(core_fwd_pipe_tc, FNT, bytes, (int)(grid.y * grid.z), "core_fwd_pipe_tc"));
   core_fwd_pipe_tc<<<grid, FNT, bytes, st>>>(a, P, ntiles, a.flags);
   LFI_LAUNCH_CHECK();
   return LFI_OK;

@@ -803,6 +803,10 @@ static int make_map(CUtensorMap *map, const __nv_bfloat16 *plane, int rows, int 
   return LFI_OK;
 }
 
+int make_plane_map(void *map, const void *plane, int rows, int cols, int ldp, long stride, int batch, int box_rows) {
+  return make_map((CUtensorMap *)map, (const __nv_bfloat16 *)plane, rows, cols, ldp, stride, batch, box_rows);
+}
+
 static int choose_bn(int N) {
   int best = 64, waste = round_up(N, 64);
   const int cand[4] = {64, 128, 192, 256};

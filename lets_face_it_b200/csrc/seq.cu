@@ -9,6 +9,7 @@
 #include "aux_kernels.cuh"
 #include "core_api.cuh"
 #include "core_pipe.cuh"
+#include "enc_persist.cuh"
 #include <cstdlib>
 
 namespace lfi {
@@ -201,6 +202,40 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
   w->bytes = round_up_sz(b.off, 256);
 }
 
+// Side streams / events of the fork-join sections (encoder chains, weight-gradient GEMMs).  They belong to a device: one
+// lazily created set per device ordinal (a second model on another device of the same process gets its own), never destroyed
+// (process lifetime, like the cached function attributes).
+struct DevRes {
+  bool init = false;
+  cudaStream_t enc_side[LFI_NMOD] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t enc_fork = nullptr, enc_join[LFI_NMOD] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t wg_stream = nullptr;
+  cudaEvent_t wg_fork = nullptr, wg_join = nullptr, ev_dc = nullptr, ev_unfold = nullptr;
+};
+static int dev_res(DevRes **out) {
+  constexpr int kMaxDev = 64;
+  static DevRes res[kMaxDev];
+  int dev = 0;
+  LFI_CUDA(cudaGetDevice(&dev));
+  LFI_REQUIRE(dev >= 0 && dev < kMaxDev, LFI_ERR_ARG, "device ordinal %d out of range", dev);
+  DevRes &r = res[dev];
+  if (!r.init) {
+    for (int i = 0; i < LFI_NMOD; ++i) {
+      LFI_CUDA(cudaStreamCreateWithFlags(&r.enc_side[i], cudaStreamNonBlocking));
+      LFI_CUDA(cudaEventCreateWithFlags(&r.enc_join[i], cudaEventDisableTiming));
+    }
+    LFI_CUDA(cudaEventCreateWithFlags(&r.enc_fork, cudaEventDisableTiming));
+    LFI_CUDA(cudaStreamCreateWithFlags(&r.wg_stream, cudaStreamNonBlocking));
+    LFI_CUDA(cudaEventCreateWithFlags(&r.wg_fork, cudaEventDisableTiming));
+    LFI_CUDA(cudaEventCreateWithFlags(&r.wg_join, cudaEventDisableTiming));
+    LFI_CUDA(cudaEventCreateWithFlags(&r.ev_dc, cudaEventDisableTiming));
+    LFI_CUDA(cudaEventCreateWithFlags(&r.ev_unfold, cudaEventDisableTiming));
+    r.init = true;
+  }
+  *out = &r;
+  return LFI_OK;
+}
+
 // Encoders + "enc: none" windows into the folded feature matrix cond[M][Fe] for frames
 // t = t0 .. t0+Tp-1 (ModalityEncoder / FeatureEncoder, models.py:55-80, 127-145).
 //   x stream m: [B][Tx][dim] ;  skip_p1: leave the p1_face columns alone (autoregressive sampler)
@@ -241,6 +276,21 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
   auto chain = [&](int m, cudaStream_t cs) -> int {
     const int hist = s->hist[m], E = s->ehid[m];
     EncWs &ew = enc[m];
+    if (ew.planes && encp::fwd_supported(E, hist, M, mode)) {
+      // persistent window GRU: all `hist` steps of a 128-window tile in one launch, state resident in shared memory
+      encp::FwdArgs a;
+      memset(&a, 0, sizeof(a));
+      a.E = E; a.hist = hist; a.B = B; a.T = T; a.t0 = t0; a.M = (int)M; a.nplanes = lo ? 2 : 1;
+      a.xp = ew.xp; a.b_ih = p->enc_b_ih[m]; a.b_hh = p->enc_b_hh[m]; a.mask = bt->mask[m];
+      a.whh_hi = ew.whh_hi; a.whh_lo = lo ? ew.whh_lo : nullptr;
+      a.stash = stash ? 1 : 0;
+      if (stash) {
+        a.hs = ew.hs; a.hp_hi = ew.hp_hi; a.hp_lo = lo ? ew.hp_lo : nullptr;
+        a.gates = ew.gates; a.gates16 = ew.gates16 ? 1 : 0; a.ahn = ew.ahn;
+      }
+      a.cond = cond + d.enc_offe[m]; a.cond_ld = d.Fe;
+      return encp::launch_fwd(a, cs);
+    }
     for (int sidx = 0; sidx < hist; ++sidx) {
       float *hprev = nullptr, *hcur;
       const int cur = stash ? sidx : (sidx & 1), prv = stash ? sidx - 1 : ((sidx - 1) & 1);
@@ -282,20 +332,15 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
     }
     return LFI_OK;
   };
-  static cudaStream_t side[LFI_NMOD] = {nullptr, nullptr, nullptr, nullptr};
-  static cudaEvent_t ev_fork = nullptr, ev_join[LFI_NMOD] = {nullptr, nullptr, nullptr, nullptr};
   const bool par = nmods > 1 && all_fused && env_flag("LFI_ENC_STREAMS", true);
   if (!par) {
     for (int i = 0; i < nmods; ++i) LFI_TRY(chain(mods[i], st));
     return LFI_OK;
   }
-  if (!ev_fork) {
-    LFI_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    for (int i = 0; i < LFI_NMOD; ++i) {
-      LFI_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
-      LFI_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
-    }
-  }
+  DevRes *dr = nullptr;
+  LFI_TRY(dev_res(&dr));
+  cudaStream_t *side = dr->enc_side;
+  cudaEvent_t ev_fork = dr->enc_fork, *ev_join = dr->enc_join;
   LFI_CUDA(cudaEventRecord(ev_fork, st));
   for (int i = 1; i < nmods; ++i) LFI_CUDA(cudaStreamWaitEvent(side[i], ev_fork, 0));
   int rc = LFI_OK;
@@ -460,16 +505,13 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   //    plane form (no shared scratch) they are independent of the rest of the backward pass: they run on a side stream,
   //    concurrently with the cond_transform / encoder backward below (small-output long-K launches and a latency-bound
   //    chain fill each other's idle SMs), and are joined before the call returns.
-  static cudaStream_t wg_stream = nullptr;
-  static cudaEvent_t wg_fork = nullptr, wg_join = nullptr;
+  DevRes *dr = nullptr;
+  LFI_TRY(dev_res(&dr));
+  cudaStream_t wg_stream = dr->wg_stream;
+  cudaEvent_t wg_fork = dr->wg_fork, wg_join = dr->wg_join;
   const bool wg_par = w.cp && env_flag("LFI_WGRAD_STREAM", true);
   cudaStream_t st_main = st;
   if (wg_par) {
-    if (!wg_stream) {
-      LFI_CUDA(cudaStreamCreateWithFlags(&wg_stream, cudaStreamNonBlocking));
-      LFI_CUDA(cudaEventCreateWithFlags(&wg_fork, cudaEventDisableTiming));
-      LFI_CUDA(cudaEventCreateWithFlags(&wg_join, cudaEventDisableTiming));
-    }
     LFI_CUDA(cudaEventRecord(wg_fork, st_main));
     LFI_CUDA(cudaStreamWaitEvent(wg_stream, wg_fork, 0));
     st = wg_stream;
@@ -529,8 +571,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
       wc_side = side_off + gemm_ws_bytes_for(gemm_mode, r) <= gws_bytes;
     }
     if (wc_side) {
-      static cudaEvent_t ev_dc = nullptr;
-      if (!ev_dc) LFI_CUDA(cudaEventCreateWithFlags(&ev_dc, cudaEventDisableTiming));
+      cudaEvent_t ev_dc = dr->ev_dc;
       LFI_CUDA(cudaEventRecord(ev_dc, st));
       LFI_CUDA(cudaStreamWaitEvent(wg_stream, ev_dc, 0));
       LFI_TRY(gemm_dispatch(bmode, r, (char *)gws + side_off, gws_bytes - side_off, wg_stream));
@@ -541,8 +582,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
       LFI_TRY(aux::unfold_wc_grad(g->wc, w.dWcF, d, *s, st));
       if (g_grad_ready_event) {  // data parallel: every flow-step weight gradient is final here, once the side-stream GEMMs are too
         if (wg_par) {  // record on the side stream, ordered after this point of the main stream (no early join of the main stream)
-          static cudaEvent_t ev_unfold = nullptr;
-          if (!ev_unfold) LFI_CUDA(cudaEventCreateWithFlags(&ev_unfold, cudaEventDisableTiming));
+          cudaEvent_t ev_unfold = dr->ev_unfold;
           LFI_CUDA(cudaEventRecord(ev_unfold, st));
           LFI_CUDA(cudaStreamWaitEvent(wg_stream, ev_unfold, 0));
           LFI_CUDA(cudaEventRecord(g_grad_ready_event, wg_stream));
@@ -630,21 +670,14 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   bool all_planes = true;
   for (int m = 0; m < LFI_NMOD; ++m)
     if (s->hist[m] > 0 && s->ehid[m] > 0) { mods[nmods++] = m; all_planes = all_planes && w.enc[m].planes; }
-  static cudaStream_t side[LFI_NMOD] = {nullptr, nullptr, nullptr, nullptr};
-  static cudaEvent_t ev_fork = nullptr, ev_join[LFI_NMOD] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t *side = dr->enc_side;
+  cudaEvent_t ev_fork = dr->enc_fork, *ev_join = dr->enc_join;
   const bool par = nmods > 1 && all_planes && env_flag("LFI_ENC_STREAMS", true);
   if (!par) {
     int rc = LFI_OK;
     for (int i = 0; i < nmods && rc == LFI_OK; ++i) rc = enc_bwd(mods[i], st);
     join_wgrads();
     return rc;
-  }
-  if (!ev_fork) {
-    LFI_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    for (int i = 0; i < LFI_NMOD; ++i) {
-      LFI_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking));
-      LFI_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
-    }
   }
   LFI_CUDA(cudaEventRecord(ev_fork, st));
   for (int i = 1; i < nmods; ++i) LFI_CUDA(cudaStreamWaitEvent(side[i], ev_fork, 0));

@@ -44,6 +44,20 @@ def _align(n, a=64):
     return (n + a - 1) // a * a
 
 
+def _on_own_device(fn):
+    """Runs an Engine method with the engine's device current: the C side launches on the current device and
+    `cabi.stream_ptr()` is the current stream of the current device, while every pointer lives on `theta.device` (a model
+    moved to cuda:1 without `torch.cuda.set_device(1)` would otherwise launch on device 0 against device 1 memory)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        self.ensure()  # (re)binds theta to the device the parameters live on now
+        with torch.cuda.device(self.theta.device):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 class Engine:
     """One engine per top-level module (SeqGlow, or a stand-alone Glow/FlowNet/FlowStep)."""
 
@@ -140,13 +154,27 @@ class Engine:
         self.n_theta = off
         # constants of the LU parametrisation (buffers, modules.py:137-138) and composed weights
         K, C = self.K, self.C
-        if self.LU and self.steps:
-            self.perm = torch.stack([st.invconv.p.detach().to(device=device, dtype=torch.float32) for st in self.steps]).contiguous()
-            self.sign_s = torch.stack([st.invconv.sign_s.detach().to(device=device, dtype=torch.float32) for st in self.steps]).contiguous()
+        self._lu_key = None
+        self._sync_lu_buffers(device)
         self.W = torch.empty(K, C, C, dtype=torch.float32, device=device)
         self.Winv = torch.empty(K, C, C, dtype=torch.float32, device=device)
         self._derived = torch.empty(cabi.lib().lfi_derived_bytes(ctypes.byref(self.shape)), dtype=torch.uint8, device=device)
         self._ws.clear()
+
+    def _sync_lu_buffers(self, device=None):
+        """Stacks the LU constants `invconv.p` / `invconv.sign_s` (buffers, modules.py:137-138) into [K,C,C] / [K,C].
+        They are not part of theta: `load_state_dict` (or `.to()`) after the engine exists replaces them behind its back, so
+        every refresh() compares their (storage, version) and re-stacks when any changed."""
+        if not (self.LU and self.steps):
+            return
+        key = tuple((st.invconv.p.data_ptr(), st.invconv.p._version, st.invconv.sign_s.data_ptr(), st.invconv.sign_s._version)
+                    for st in self.steps)
+        if key == self._lu_key:
+            return
+        device = device or self.theta.device
+        self.perm = torch.stack([st.invconv.p.detach().to(device=device, dtype=torch.float32) for st in self.steps]).contiguous()
+        self.sign_s = torch.stack([st.invconv.sign_s.detach().to(device=device, dtype=torch.float32) for st in self.steps]).contiguous()
+        self._lu_key = key
 
     def block(self, name, flat=None):
         off, n, k = self.blocks[name]
@@ -174,17 +202,25 @@ class Engine:
         return P
 
     def _workspace(self, key, nbytes):
-        t = self._ws.get(key)
+        """ONE grow-only buffer per kind (key[0]: "train", "sample", "feat", ...): a validation shape, a partial last batch
+        or a different chunk reuses it when it is large enough and replaces it when it is not (a workspace per (B, T) key
+        would keep several multi-GB buffers alive for the life of the model)."""
+        kind = key[0]
+        t = self._ws.get(kind)
         if t is None or t.numel() < nbytes:
+            self._ws.pop(kind, None)
+            t = None  # release the old buffer before allocating the larger one
             t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.theta.device)
-            self._ws[key] = t
+            self._ws[kind] = t
         return t
 
     # ------------------------------------------------------------------ derived state
+    @_on_own_device
     def refresh(self, need_inverse=False):
         """Composes W (and W^-1) from the LU parameters and rebuilds the derived weight cache.
         Call after every parameter change (done at the top of each forward / inference)."""
         self.ensure()
+        self._sync_lu_buffers()
         L, st = cabi.lib(), cabi.stream_ptr()
         K, C = self.K, self.C
         if self.LU:
@@ -247,6 +283,7 @@ class Engine:
         return bt, keep
 
     # ------------------------------------------------------------------ SeqGlow.forward / backward
+    @_on_own_device
     def train_forward(self, batch, masks=None, scale_out=None):
         """Returns (z [T',B,C], nll_core [T',B]); nll_core lacks the parameter-only log-det constant."""
         P = self.refresh(False)
@@ -268,6 +305,7 @@ class Engine:
         self._last = (bt, keep, B, T, P)
         return z, nll
 
+    @_on_own_device
     def train_backward(self, z, dnll, gflat, token=None):
         """Accumulates dL/dtheta into gflat (layout of new_flat_grad) given dL/dnll [T',B]."""
         if token is not None and token != self._fwd_token:
@@ -308,6 +346,7 @@ class Engine:
         return [p for p, _, _ in self._views]
 
     # ------------------------------------------------------------------ SeqGlow.inference / invert
+    @_on_own_device
     def sample(self, data, seq_len, noise=None, teacher_forced=False, chunk=None, want_logdet=False):
         """faces [B, seq_len, C]: seed in [:, :start_ts], generated (or reconstructed) frames after."""
         P = self.refresh(True)
@@ -356,6 +395,7 @@ class Engine:
         return faces, logdet
 
     # ------------------------------------------------------------------ module-level API
+    @_on_own_device
     def feature_encode(self, data, t0, Tp, masks=None):
         """Folded FeatureEncoder output [Tp*B, Fe] for frames t0..t0+Tp-1 of a batch dict."""
         self.ensure()
@@ -383,6 +423,7 @@ class Engine:
             off += w
         return torch.cat(parts, dim=1)
 
+    @_on_own_device
     def flowstep(self, k, x, cond, h_in, c_in, logdet, reverse, want_scale=False, refresh=True):
         """One FlowStep on one frame (models.py:305-373).  Returns (y, logdet, h, c, scale)."""
         if refresh:

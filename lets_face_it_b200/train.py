@@ -19,12 +19,20 @@ LN2 = math.log(2.0)
 
 
 class Trainer:
-    def __init__(self, model, lr=None, betas=None, eps=None, max_norm=None, process_group=None, dropout=True):
+    def __init__(self, model, lr=None, betas=None, eps=None, max_norm=None, process_group=None, dropout=True, probe_seed=1234):
         hp = model.hparams
         self.model = model
         self.eng = model.engine()
         adam = hp.Optim["args"]["adam"]
-        self.lr = float(lr if lr is not None else hp.lr)
+        self.base_lr = float(lr if lr is not None else hp.lr)
+        self.lr = self.base_lr
+        self.epoch = 0
+        # configure_optimizers (lets_face_it_glow.py:61-72) returns get_scheduler(Optim.Schedule) (utils.py:65-82): StepLR per epoch
+        sched = (hp.Optim.get("Schedule") or {}) if isinstance(getattr(hp, "Optim", None), dict) else {}
+        self._sched_name = sched.get("name") or None
+        self._sched_args = (sched.get("args") or {}).get(self._sched_name, {}) if self._sched_name else {}
+        if self._sched_name not in (None, "step"):
+            raise NotImplementedError("Unimplemented Scheduler!")  # utils.py:80 (multiplicative / lambda are unused by the shipped yamls)
         self.betas = tuple(betas if betas is not None else adam["betas"])
         self.eps = float(eps if eps is not None else adam["eps"])
         self.max_norm = float(max_norm if max_norm is not None else (hp.gradient_clip_val or 0))
@@ -40,6 +48,10 @@ class Trainer:
         self.world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(process_group)
+        # the probe decision of training_step must be the same on every rank: a generator of its own,
+        # seeded identically everywhere, instead of the process-global `random` whose state differs between ranks
+        import random
+        self._probe_rng = random.Random(probe_seed) if self.world > 1 else random
         self._dnll = {}
         # LetsFaceItGlow.__init__ (lets_face_it_glow.py:28-36): state of the mismatched-NLL probe
         self.last_missmatched_nll = float("inf")
@@ -56,9 +68,18 @@ class Trainer:
             self._bucket = flow_grad_range(self.eng.blocks)
 
     def broadcast_parameters(self, src=0):
-        """Replicas start identical (and share the ActNorm data-dependent init of rank `src`)."""
+        """Replicas start identical.  (The ActNorm data-dependent init is shared by `step` itself: it broadcasts rank 0's
+        parameters right after the init, whatever the caller did before.)"""
         if self.world > 1:
             torch.distributed.broadcast(self.eng.theta, src, group=self.pg)
+
+    def epoch_end(self):
+        """StepLR(step_size, gamma) stepped once per epoch, as Lightning steps the scheduler `configure_optimizers` returns
+        (lets_face_it_glow.py:61-72, utils.py:65-82; final_model.yaml: step_size 3, gamma 0.73)."""
+        self.epoch += 1
+        if self._sched_name == "step":
+            self.lr = self.base_lr * float(self._sched_args.get("gamma", 0.1)) ** (self.epoch // int(self._sched_args["step_size"]))
+        return self.lr
 
     def training_step(self, batch, masks=None):
         """`LetsFaceItGlow.training_step` (lets_face_it_glow.py:39-55) on the fused step: with `use_negative_nll_loss`, once
@@ -66,22 +87,25 @@ class Trainer:
         interlocutor modalities are shuffled across sequences (`derange_batch`) with the loss scaled by -0.1.  The `and`
         chain is evaluated in the reference's order, so `random.random()` is consumed on the same steps; the only host
         synchronisation is the read-back of the probe's NLL on those (10 %) steps.  Returns (loss, deranged)."""
-        import random
-
         from .glow.utils import derange_batch
 
         hp = self.model.hparams
-        if (hp.Train["use_negative_nll_loss"] and self.last_missmatched_nll > 0 and random.random() < 0.1
+        if (hp.Train["use_negative_nll_loss"] and self.last_missmatched_nll > 0 and self._probe_rng.random() < 0.1
                 and self.missmatched_modalities):
             loss = self.step(derange_batch(batch, self.missmatched_modalities), masks, loss_scale=-0.1)
-            self.last_missmatched_nll = -float(loss)  # "Loss/missmatched_nll" (:51-52)
+            probe = loss.detach().clone()
+            if self.world > 1:  # every rank must see the same `last_missmatched_nll`: mean over the global batch
+                torch.distributed.all_reduce(probe, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+                probe /= self.world
+            self.last_missmatched_nll = -float(probe)  # "Loss/missmatched_nll" (:51-52)
             return loss * -0.1, True
         return self.step(batch, masks), False
 
     def step(self, batch, masks=None, loss_scale=1.0):
         """One optimizer step on this rank's shard of sequences.  Returns the (device) loss of the shard (unscaled);
         `loss_scale` multiplies the loss the gradient is taken of (the -0.1 of the mismatched-NLL probe)."""
-        eng, model = self.eng, self.model
+        model = self.model
+        eng = self.eng = model.engine()  # picks up a changed model.gemm_mode / a model moved to another device
         x0 = batch["p1_face"]
         B, T = x0.shape[0], x0.shape[1]
         Tp = T - eng.start_ts
@@ -89,6 +113,8 @@ class Trainer:
             masks = model._masks(Tp, B, eng.theta.device)
         if model.training and not all(l.actnorm.inited for l in model.glow.flow.layers):
             model._ddi(eng, batch, masks)
+            if self.world > 1:  # the init is data dependent: every replica takes rank 0's (the other shards' statistics are dropped)
+                torch.distributed.broadcast(eng.theta, 0, group=self.pg)
         z, nll = eng.train_forward(batch, masks)
         key = (Tp, B, float(loss_scale))
         if key not in self._dnll:

@@ -129,8 +129,9 @@ def actnorm_ddi(P, pre, x, scale):
     bias = -x.mean(dim=0, keepdim=True)
     var = ((x + bias) ** 2).mean(dim=0, keepdim=True)
     logs = torch.log(scale / (torch.sqrt(var) + 1e-6))
-    P[pre + "bias"] = bias.detach().clone()
-    P[pre + "logs"] = logs.detach().clone()
+    for name, val in (("bias", bias), ("logs", logs)):  # `.data.copy_` in the reference: the parameter stays a trainable leaf
+        old = P.get(pre + name)
+        P[pre + name] = val.detach().clone().requires_grad_(bool(old is not None and old.requires_grad))
 
 
 def invconv_weight(P, pre, C, reverse, LU=True):

@@ -172,6 +172,12 @@ def run_case(hp, B, T, infer_len, with_masks, full_tensors, tag):
             out["masked_z"] = torch.stack(z_seq_m).numpy()
             for n, p in m.named_parameters():
                 out["masked_grad/" + n] = p.grad.numpy().copy()
+        else:
+            out["masked_z_head"] = torch.stack(z_seq_m)[:, :min(B, 8)].numpy()
+            out["masked_z_sum"] = np.float64(torch.stack(z_seq_m).double().sum())
+        out["masked_grad_total_norm"] = np.float64(np.sqrt((out["masked_grad_norms"] ** 2).sum()))
+        for mod_name, fd in feeders.items():  # back to "dropout disabled" for whatever follows
+            getattr(m.feature_encoder, mod_name + "_encoder").dropout = None
 
     names, fp = fingerprint(sd)
     out["fp_names"] = np.array(names)
@@ -209,6 +215,97 @@ def run_case(hp, B, T, infer_len, with_masks, full_tensors, tag):
           "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def run_long_sampling(hp, B, gen_frames, keep, tag):
+    """BASELINE.json configs[3] horizon: `SeqGlow.inference` (models.py:567-596) of 30 s = 750 frames at temperature 0.7 with
+    injected noise (Generator(21), so the GPU test regenerates it), zero seed frames, KAT model after the DDI pass of the
+    B=64 KAT batch.  Stores the first `keep` sequences (sequences are independent)."""
+    models, modules = import_reference()
+    hy = O.Hyper.from_hparams(hp)
+    m = build_reference_model(hp, models, modules)
+    m.train()
+    m(O.synthetic_batch(hy, 64, 80, seed=1))  # the DDI pass of kat_full
+    m.eval()
+    seq_len = hy.start_ts + gen_frames
+    data = O.synthetic_batch(hy, B, seq_len, seed=5)
+    data["p1_face"] = torch.zeros(B, hy.start_ts, hy.C)
+    noise = torch.randn(gen_frames, B, hy.C, generator=torch.Generator().manual_seed(21)) * 0.7
+    it = iter(noise)
+    orig = modules.GaussianDiag.sample
+    modules.GaussianDiag.sample = staticmethod(lambda shape, eps_std=1: next(it))
+    try:
+        hp.Infer["eps"] = 0.7
+        x = m.inference(seq_len, data=data)
+    finally:
+        modules.GaussianDiag.sample = orig
+    out = {"B": B, "gen_frames": gen_frames, "x_head": x[:keep].numpy(), "x_sum": np.float64(x.double().sum()),
+           "x_absmax_per_frame": x.abs().amax(dim=(0, 2)).numpy()}
+    for k, v in m.state_dict().items():
+        if ".actnorm." in k:
+            out["param/" + k] = v.numpy()
+    path = os.path.join(GOLDEN, tag + ".npz")
+    np.savez_compressed(path, **out)
+    print(tag, "max|x|", float(x.abs().max()), "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+def run_train_steps(hp, B, T, steps, with_masks, full_tensors, tag):
+    """`steps` optimizer steps of the reference's training loop on the live reference: `LetsFaceItGlow.training_step` is
+    `loss = seq_glow(batch)[1]` (lets_face_it_glow.py:52), Lightning then runs backward, `clip_grad_norm_(gradient_clip_val)`
+    (final_model.yaml:126) and `configure_optimizers`' Adam(lr, betas, eps) (lets_face_it_glow.py:61-72, final_model.yaml:91-95,
+    130).  The first step includes the ActNorm DDI (model fresh, training mode).  Stores the loss of every step, the global
+    gradient norm before clipping, and theta_after - theta_before per tensor (full tensors for the small case, fingerprints
+    plus a few whole tensors for final_model.yaml)."""
+    models, modules = import_reference()
+    hy = O.Hyper.from_hparams(hp)
+    m = build_reference_model(hp, models, modules)
+    batch = O.synthetic_batch(hy, B, T, seed=1)
+    Tp = T - hy.start_ts
+    if with_masks:
+        masks_per_step = [O.make_masks(hy, B, Tp, seed=30 + st) for st in range(steps)]
+    m.train()
+    adam = hp.Optim["args"]["adam"]
+    opt = torch.optim.Adam(m.parameters(), lr=hp.lr, betas=tuple(adam["betas"]), eps=adam["eps"])
+    out = {"B": B, "T": T, "steps": steps, "lr": np.float64(hp.lr), "with_masks": int(with_masks)}
+    theta0 = None
+    losses, gnorms = [], []
+    for st in range(steps):
+        if with_masks:
+            for mod_name in O.MODALITIES:
+                enc = getattr(m.feature_encoder, mod_name + "_encoder", None)
+                if enc is not None and masks_per_step[st][mod_name] is not None:
+                    enc.dropout = _MaskFeeder(masks_per_step[st][mod_name])
+        opt.zero_grad()
+        loss = m(batch)[1]
+        if theta0 is None:  # after the DDI of the first forward: ActNorm parameters are data dependent
+            theta0 = {n: p.detach().clone() for n, p in m.named_parameters()}
+        loss.backward()
+        gn = torch.nn.utils.clip_grad_norm_(m.parameters(), hp.gradient_clip_val)
+        opt.step()
+        losses.append(float(loss))
+        gnorms.append(float(gn))
+        print(tag, "step", st, "loss", float(loss), "grad norm", float(gn))
+    out["losses"] = np.array(losses, dtype=np.float64)
+    out["grad_norms"] = np.array(gnorms, dtype=np.float64)
+    names = [n for n, _ in m.named_parameters()]
+    out["names"] = np.array(names)
+    delta = {n: (p.detach() - theta0[n]) for n, p in m.named_parameters()}
+    out["delta_l2"] = np.array([float(delta[n].double().norm()) for n in names])
+    out["delta_sum"] = np.array([float(delta[n].double().sum()) for n in names])
+    keep_full = names if full_tensors else [n for n in names if n.endswith(("layers.0.actnorm.logs", "layers.0.invconv.log_s", "layers.7.f.final_linear.weight",
+                                                                              "layers.15.f.rnn.weight_hh", "p1_speech_encoder.encoder.weight_hh_l0",
+                                                                              "layers.3.f.rnn.bias_ih"))]
+    for n in keep_full:
+        out["delta/" + n] = delta[n].numpy()
+    for n, p in theta0.items():
+        if full_tensors or ".actnorm." in n:
+            out["theta0/" + n] = p.numpy()
+    if full_tensors:
+        for k, v in batch.items():
+            out["batch/" + k] = v.numpy()
+    path = os.path.join(GOLDEN, tag + ".npz")
+    np.savez_compressed(path, **out)
+    print(tag, "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -220,7 +317,12 @@ def main():
     if a.only in ("", "small_lstm"):
         run_case(small_hparams("lstm"), B=6, T=12, infer_len=12, with_masks=True, full_tensors=True, tag="kat_small_lstm")
     if a.only in ("", "full"):
-        run_case(load_reference_hparams(), B=64, T=80, infer_len=80, with_masks=False, full_tensors=False, tag="kat_full")
+        run_case(load_reference_hparams(), B=64, T=80, infer_len=80, with_masks=True, full_tensors=False, tag="kat_full")
+    if a.only in ("", "long"):
+        run_long_sampling(load_reference_hparams(), B=16, gen_frames=750, keep=4, tag="kat_long")
+    if a.only in ("", "steps"):
+        run_train_steps(small_hparams("gru"), B=6, T=12, steps=3, with_masks=True, full_tensors=True, tag="kat_steps_small")
+        run_train_steps(load_reference_hparams(), B=64, T=80, steps=3, with_masks=False, full_tensors=False, tag="kat_steps_full")
 
 
 if __name__ == "__main__":

@@ -159,3 +159,40 @@ def test_tensor_core_sampler_matches_fp32_sampler(mode, tol):
     sl = {k: v[:8].cpu() for k, v in data.items()}
     x_ref = O.seq_inference(P, hy, sl, T, noise=noise[:, :8].cpu())
     assert relerr(xtc[:8], x_ref) < tol
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 2e-5), ("bf16", 5e-3)])
+@pytest.mark.parametrize("B", [256, 100])
+def test_persistent_encoder_matches_per_step_launches(mode, tol, B):
+    """The persistent window-GRU kernel (enc_persist.cu: all 24 / 2 / 16 window steps of a 128-window tile in one launch, state
+    resident in shared memory, halves exchanged through DSMEM) against round 1's chain of per-step launches
+    (LFI_ENC_PERSIST=0): encoded features, z / NLL and every gradient (the backward pass reads the stash the forward kernel
+    wrote).  Frame-dropout masks on.  B=100 leaves a ragged last tile (5,600 rows = 43.75 tiles)."""
+    hp, m = _model(mode)
+    hy = O.Hyper.from_hparams(hp)
+    m.train()
+    T = 80
+    batch = to_device(kat_batch(hp, B, T, seed=31), DEV)
+    masks = O.make_masks(hy, B, T - hy.start_ts, seed=32)
+    m.injected_masks = {k: (v.to(DEV) if v is not None else None) for k, v in masks.items()}
+    eng = m.engine()
+    c1 = eng.feature_encode(batch, hy.start_ts, T - hy.start_ts, m.injected_masks).clone()
+    z1, n1, g1 = _fwd_bwd(m, batch)
+    with _env(LFI_ENC_PERSIST="0"):
+        c0 = eng.feature_encode(batch, hy.start_ts, T - hy.start_ts, m.injected_masks).clone()
+        z0, n0, g0 = _fwd_bwd(m, batch)
+    assert relerr(c1, c0) < tol
+    assert relerr(z1, z0) < 5 * tol
+    assert relerr(n1, n0) < 1e-5 if mode == "bf16x3" else 1e-4
+    for k in g0:
+        ref = g0[k].double()
+        err = float((g1[k].double() - ref).norm() / ref.norm().clamp_min(1e-30))
+        assert err < (2e-3 if mode == "bf16x3" else 0.1), (k, err)
+    # and the encoded features against the oracle on 8 sequences of the first two frames
+    P = {k: v.detach() for k, v in oracle_params_from(m).items()}
+    S = 8
+    for ti in (0, 1):
+        msl = {k: (v[:, :S].contiguous() if v is not None else None) for k, v in masks.items()}
+        ref = O.conditioning(P, hy, {k: v[:S].cpu() for k, v in batch.items()}, hy.start_ts + ti, batch["p1_face"][:S].cpu(), msl, ti)
+        got = eng.unfold_features(c1[ti * B: ti * B + S]).cpu()
+        assert relerr(got, ref) < (1e-4 if mode == "bf16x3" else 5e-3)
