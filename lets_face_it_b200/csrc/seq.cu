@@ -91,6 +91,11 @@ struct EncWs {
   void *xg_hi, *xg_lo;    // masked window inputs [hist][M][round_up(dim, 8)]
   float *xg32;            // the same in fp32 [hist][M][dim] (split source / fp32-mode operand)
   float *dhe;             // [M][E] running d h of the window recurrence
+  // persistent window-GRU kernels (enc_persist.cu): xp is time-major and row-interleaved, the stash (hs, gates, ahn, dhe) is
+  // row-interleaved with rows padded to 32, dah holds gate-interleaved columns
+  bool persist;
+  float *xT;              // [T*B][dim] raw frames in time-major order (input of the projection GEMM)
+  float *wscr;            // [3E][E + round_up(dim, 8)] weight gradients over gate-interleaved rows, before de-interleaving
 };
 
 // A modality's encoder runs on operand planes when every GEMM it issues is taken by the tcgen05 tiles.
@@ -99,6 +104,15 @@ static bool enc_use_planes(const lfi_shape *s, int m, size_t M, int mode) {
   const int E = s->ehid[m], dim = s->dim[m];
   if (E < 32 || E % 8 != 0 || dim < 16 || M < 128) return false;
   GemmArgs g = gemm_args(0, 1, (int)M, 3 * E, E, nullptr, E, nullptr, E, nullptr, 3 * E);
+  return gemm_tc_wants(g);
+}
+// The persistent window-GRU kernels take over a modality when its encoder runs on operand planes, the shape fits them and the
+// projection GEMM is taken by the tcgen05 tiles (only those write the row-interleaved xp).
+static bool enc_use_persist(const lfi_shape *s, int m, size_t M, size_t BT, int mode, bool need_bwd) {
+  if (!enc_use_planes(s, m, M, mode)) return false;
+  const int E = s->ehid[m], hist = s->hist[m];
+  if (need_bwd ? !encp::bwd_supported(E, hist, M, mode) : !encp::fwd_supported(E, hist, M, mode)) return false;
+  GemmArgs g = gemm_args(0, 1, (int)BT, 3 * E, s->dim[m], nullptr, s->dim[m], nullptr, s->dim[m], nullptr, 3 * E);
   return gemm_tc_wants(g);
 }
 static void *take_bf16(Bump &b, size_t n) { return (void *)b.take<uint16_t>(n); }
@@ -141,11 +155,15 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
     if (s->hist[m] <= 0 || s->ehid[m] <= 0) continue;
     const size_t E = s->ehid[m], h = s->hist[m];
     EncWs &e = w->enc[m];
-    e.xp = b.take<float>((size_t)B * T * 3 * E);
-    e.hs = b.take<float>(h * M * E);
-    e.gates = b.take<float>(h * M * 3 * E);
-    e.ahn = b.take<float>(h * M * E);
+    const size_t Mp = encp::tiled_rows(M);
+    e.xp = b.take<float>(encp::tiled_rows((size_t)B * T) * 3 * E);
+    e.hs = b.take<float>(h * Mp * E);
+    e.gates = b.take<float>(h * Mp * 3 * E);
+    e.ahn = b.take<float>(h * Mp * E);
     e.planes = enc_use_planes(s, m, M, mode);
+    e.persist = enc_use_persist(s, m, M, (size_t)B * T, mode, true);
+    e.xT = e.persist ? b.take<float>((size_t)B * T * s->dim[m]) : nullptr;
+    e.wscr = e.persist ? b.take<float>(3 * E * (E + round_up(s->dim[m], 8))) : nullptr;
     e.gates16 = e.planes && E % 4 == 0 && env_flag("LFI_GATES16", true) && !env_flag("LFI_FUSED_GRU_BWD", false);
     if (e.planes) {
       const bool lo = mode == LFI_GEMM_BF16X3;
@@ -160,7 +178,7 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
       e.dan32 = b.take<float>(h * M * E);
     }
     e.xg32 = b.take<float>(h * M * s->dim[m]);
-    e.dhe = b.take<float>(M * E);
+    e.dhe = b.take<float>(Mp * E);
     if (M * 3 * E > ghmax) ghmax = M * 3 * E;
     if (h * M * s->dim[m] > xgmax) xgmax = h * M * s->dim[m];
     if (E > emax) emax = E;
@@ -260,7 +278,13 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
       continue;
     }
     // input projection for every raw frame (window independent): xp = x @ W_ih^T
-    if (project) {
+    if (project && enc[m].persist) {
+      // raw frames in time-major order (row tau * B + b), projected into the row-interleaved layout the persistent kernel reads
+      LFI_TRY(aux::gather_windows(enc[m].xT, dim, 1, bt->x[m], nullptr, B, T, dim, 1, 1, 0, T, st));
+      GemmArgs g = gemm_args(0, 1, B * T, 3 * E, dim, enc[m].xT, dim, p->enc_w_ih[m], dim, enc[m].xp, 3 * E);
+      g.c_tiled32 = 1;
+      LFI_TRY(gemm_dispatch(mode, g, gws, gws_bytes, st));
+    } else if (project) {
       GemmArgs g = gemm_args(0, 1, B * T, 3 * E, dim, bt->x[m], dim, p->enc_w_ih[m], dim, enc[m].xp, 3 * E);
       LFI_TRY(gemm_dispatch(mode, g, gws, gws_bytes, st));
     }
@@ -268,7 +292,7 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
     if (ew.planes && project)  // W_hh planes: once per call (weights change every optimizer step)
       LFI_TRY(split_to_planes(p->enc_w_hh[m], 3 * E, E, E, 0, 1, ew.whh_hi, lo ? ew.whh_lo : nullptr, st));
     mods[nmods++] = m;
-    all_fused = all_fused && ew.planes && E % 64 == 0 && env_flag("LFI_FUSED_GRU_FWD", true);
+    all_fused = all_fused && ew.planes && (ew.persist || (E % 64 == 0 && env_flag("LFI_FUSED_GRU_FWD", true)));
   }
   // ---- phase 2: the window recurrences.  With the fused GRU launches (operands in plane form, no shared scratch) the
   //      modalities are independent chains: they run on parallel streams forked from / joined to the caller's, so that the
@@ -276,7 +300,7 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
   auto chain = [&](int m, cudaStream_t cs) -> int {
     const int hist = s->hist[m], E = s->ehid[m];
     EncWs &ew = enc[m];
-    if (ew.planes && encp::fwd_supported(E, hist, M, mode)) {
+    if (ew.persist) {
       // persistent window GRU: all `hist` steps of a 128-window tile in one launch, state resident in shared memory
       encp::FwdArgs a;
       memset(&a, 0, sizeof(a));
@@ -617,6 +641,39 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
       LFI_TRY(aux::gather_windows_planes(ew.xg_hi, lo ? ew.xg_lo : nullptr, dimp, bt->x[m], bt->mask[m], B, T, dim, hist, 1, d.start_ts, Tp, st));
     else
       LFI_TRY(aux::gather_windows(ew.xg32, dim, 1, bt->x[m], bt->mask[m], B, T, dim, hist, 1, d.start_ts, Tp, st));
+    if (ew.persist) {
+      // persistent BPTT over the window: one launch, then the weight gradients as long-K GEMMs over the gate-interleaved planes
+      encp::BwdArgs q;
+      memset(&q, 0, sizeof(q));
+      q.E = E; q.hist = hist; q.M = (int)M; q.nplanes = lo ? 2 : 1;
+      q.hs = ew.hs; q.gates = ew.gates; q.gates16 = ew.gates16 ? 1 : 0; q.ahn = ew.ahn;
+      q.whh_hi = ew.whh_hi; q.whh_lo = lo ? ew.whh_lo : nullptr;
+      q.dh_extra = w.dcond + d.enc_offe[m]; q.dh_extra_ld = d.Fe;
+      q.dhd = ew.dhe;
+      q.dah3_hi = ew.dah_hi; q.dah3_lo = lo ? ew.dah_lo : nullptr; q.dan_hi = ew.dan_hi; q.dan_lo = lo ? ew.dan_lo : nullptr;
+      q.gb_ih = g->enc_b_ih[m]; q.gb_hh = g->enc_b_hh[m];
+      LFI_TRY(encp::launch_bwd(q, st));
+      float *s_hh = ew.wscr, *s_ih = ew.wscr + (size_t)3 * E * E;
+      LFI_TRY(aux::fill(ew.wscr, 0.f, (size_t)3 * E * (E + dimp), st));
+      const int Kall = (int)(hist * M), Khh = (int)((hist - 1) * M);
+      if (hist > 1) {  // rows 3u+g of s_hh = sum_{s>=1} dA_h[s][:, (g, u)]^T h[s-1]
+        GemmArgs r = gemm_args(1, 0, 3 * E, E, Khh, nullptr, 3 * E, nullptr, E, s_hh, E, LFI_EPI_ACCUM);
+        r.pA = plane_ref(off16(ew.dah_hi, M * 3 * E), lo ? off16(ew.dah_lo, M * 3 * E) : nullptr, 3 * E);
+        r.pB = plane_ref(ew.hp_hi, ew.hp_lo, E);
+        LFI_TRY(gemm_dispatch(bmode, r, gws, gws_bytes, st));
+        LFI_TRY(encp::add_deinterleaved_rows(g->enc_w_hh[m], s_hh, E, 3, E, st));
+      }
+      {  // r, u rows of dW_ih from the interleaved planes (the da_n r rows of the product are not used), n rows from da_n
+        GemmArgs r = gemm_args(1, 0, 3 * E, dim, Kall, nullptr, 3 * E, nullptr, dim, s_ih, dim, LFI_EPI_ACCUM);
+        r.pA = plane_ref(ew.dah_hi, ew.dah_lo, 3 * E); r.pB = plane_ref(ew.xg_hi, ew.xg_lo, dimp);
+        LFI_TRY(gemm_dispatch(bmode, r, gws, gws_bytes, st));
+        LFI_TRY(encp::add_deinterleaved_rows(g->enc_w_ih[m], s_ih, E, 2, dim, st));
+        GemmArgs n = gemm_args(1, 0, E, dim, Kall, nullptr, E, nullptr, dim, g->enc_w_ih[m] + (size_t)2 * E * dim, dim, LFI_EPI_ACCUM);
+        n.pA = plane_ref(ew.dan_hi, ew.dan_lo, E); n.pB = plane_ref(ew.xg_hi, ew.xg_lo, dimp);
+        LFI_TRY(gemm_dispatch(bmode, n, gws, gws_bytes, st));
+      }
+      return LFI_OK;
+    }
     LFI_TRY(aux::fill(ew.dhe, 0.f, M * E, st));
     const bool fused = ew.planes && (E == 64 || E == 128 || E == 192 || E == 256) && env_flag("LFI_FUSED_GRU_BWD", false);
     for (int sidx = hist - 1; sidx >= 0; --sidx) {
@@ -721,9 +778,11 @@ static void plan_sample(const lfi_shape *s, const Dims &d, int B, int T, int chu
     if (s->hist[m] <= 0 || s->ehid[m] <= 0) continue;
     const size_t E = s->ehid[m];
     EncWs &e = w->enc[m];
-    e.xp = b.take<float>((size_t)B * T * 3 * E);
+    e.xp = b.take<float>(encp::tiled_rows((size_t)B * T) * 3 * E);
     e.hs = b.take<float>(2 * Mc * E);
     e.planes = enc_use_planes(s, m, Mc, mode);
+    e.persist = enc_use_persist(s, m, Mc, (size_t)B * T, mode, false);
+    e.xT = e.persist ? b.take<float>((size_t)B * T * s->dim[m]) : nullptr;
     if (e.planes) {
       const bool lo = mode == LFI_GEMM_BF16X3;
       e.hp_hi = take_bf16(b, 2 * Mc * E);  e.hp_lo = lo ? take_bf16(b, 2 * Mc * E) : nullptr;

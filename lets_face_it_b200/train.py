@@ -139,11 +139,12 @@ class Trainer:
         else:
             eng.train_backward(z, self._dnll[key], self.gflat)
             allreduce_flat_gradient(g, self.world, self.pg)  # sum; averaged by grad_scale below
+        loss = nll.mean() - eng.logdet_const() / LN2  # before the update: the parameter-only log-det term belongs to THIS step's theta
         self.step_count += 1
         cabi.check(cabi.lib().lfi_clip_adam(eng.theta.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), eng.n_theta,
                                             self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0 / self.world,
                                             self.step_count, self.scratch.data_ptr(), cabi.stream_ptr()), "lfi_clip_adam")
-        return nll.mean() - eng.logdet_const() / LN2
+        return loss
 
     def grad_norm(self):
         """Global gradient norm of the last step (after the all-reduce average, before clipping)."""
