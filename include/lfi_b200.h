@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LFI_ABI_VERSION 3
+#define LFI_ABI_VERSION 4
 #define LFI_NMOD 4 /* p1_face, p2_face, p1_speech, p2_speech — concat order of models.py:127-145 */
 
 typedef enum lfi_status {
@@ -158,6 +158,24 @@ int lfi_flowstep(const lfi_shape *s, const void *derived, const lfi_params *p, i
                  float *c_out, float *y, float *logdet, float *scale_out, int B, void *ws, size_t ws_bytes,
                  void *stream);
 size_t lfi_flowstep_ws_bytes(const lfi_shape *s, int B);
+
+/* ---- FlowStep.forward WITH autograd (models.py:305-342 under torch autograd; test_modules.py:30-67 builds training loops on
+ * the per-frame module API).  lfi_flowstep_fwd_train = lfi_flowstep (forward direction) that also fills `stash`
+ * (lfi_flowstep_stash_bytes, caller owned, opaque) with the activations of the call; lfi_flowstep_bwd is its backward:
+ *   in : dy [B,C] = dL/d(output), dlogdet [B] = dL/d(logdet) (NULL = 0), dh_out / dc_out [B,H] = dL/d(new state) (NULL = 0),
+ *        cond [B,F] and h_in / c_in [B,H] as passed to the forward (NULL state = zeros)
+ *   out: dx [B,C], dcond [B,F], dh_in (/ dc_in) [B,H]; parameter gradients of step k are ACCUMULATED into g (layout of
+ *        lfi_params; g->w receives dL/dW of the composed 1x1 weight -> lfi_invconv_compose_bwd; the parameter-only log-det
+ *        terms C*sum(logs), C*sum(log_s) are the host's, as in lfi_seq_train_bwd). */
+size_t lfi_flowstep_stash_bytes(const lfi_shape *s, int B);
+size_t lfi_flowstep_bwd_ws_bytes(const lfi_shape *s, int B);
+int lfi_flowstep_fwd_train(const lfi_shape *s, const void *derived, const lfi_params *p, int k, const float *x, const float *cond,
+                           const float *h_in, const float *c_in, float *h_out, float *c_out, float *y, float *logdet,
+                           float *scale_out, int B, void *stash, size_t stash_bytes, void *ws, size_t ws_bytes, void *stream);
+int lfi_flowstep_bwd(const lfi_shape *s, const void *derived, const lfi_params *p, int k, const float *cond, const float *h_in,
+                     const float *c_in, const float *dy, const float *dlogdet, const float *dh_out, const float *dc_out, float *dx,
+                     float *dcond, float *dh_in, float *dc_in, lfi_params *g, int B, void *stash, size_t stash_bytes, void *ws,
+                     size_t ws_bytes, void *stream);
 
 /* ---- primitives exposed for the module API and unit parity --------------------------------- */
 /* ActNorm2d.forward (modules.py:45-80) on [B,C]: reverse=0  y=(x+bias)*exp(logs); reverse=1 y=x*exp(-logs)-bias */

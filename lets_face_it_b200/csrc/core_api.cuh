@@ -84,6 +84,17 @@ struct BwdArgs {
   void *pdG_hi, *pdG_lo, *pdAh_hi, *pdAh_lo, *pdO_hi, *pdO_lo, *pdzf_hi, *pdzf_lo;
   float *g_b_ih;
   int stash_tiled;  // st.gates / st.ahn / st.h in the tiled layout (see FwdArgs)
+  // Module API (lfi_flowstep_bwd: FlowStep.forward's autograd on ONE frame): single >= 0 runs the single cell (single, t = 0)
+  // with external seeds and outputs, all [B][width] for that step (the [K][Tp][B] arrays above are addressed through
+  // base pointers moved back by `single` cells, the way lfi_flowstep addresses its state):
+  int single;                 // -1: whole-sequence backward
+  const float *dz_ext;        // [B][C]  dL/d(output of the step)          (instead of d nll / d z)
+  const float *dld_ext;       // [B]     dL/d(logdet) or nullptr (0)       (instead of -dnll / ln2)
+  const float *dh_ext, *dc_ext;        // [B][H] dL/d(h_out), dL/d(c_out) or nullptr (0)
+  const float *h_prev_ext, *c_prev_ext;  // [B][H] state the cell started from, or nullptr (zeros)
+  float *dx0_out;             // [B][C]  dL/d(input of the step)
+  float *dh0_out, *dc0_out;   // [B][H]  dL/d(h_in), dL/d(c_in)
+  long dg_ld; int dg_k0;      // dG row pitch / first step (0: K*GH, 0)
 };
 
 int fwd_smem_bytes(const Dims &d, int R);
@@ -91,6 +102,7 @@ int choose_rpt(const Dims &d, int B, bool bwd, bool sampler);
 int launch_fwd(const FwdArgs &a, cudaStream_t st);
 int launch_inv(const InvArgs &a, cudaStream_t st);
 int launch_bwd(const BwdArgs &a, cudaStream_t st);
+int launch_bwd_single(const BwdArgs &a, cudaStream_t st);  // a.single >= 0: one cell through the wavefront kernel
 bool inv_rows_supported(const InvArgs &a);
 int launch_inv_rows(const InvArgs &a, cudaStream_t st);
 

@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
     if (r < nrows) {
       const int b = row0 + r;
       zf = a.st.zf[(cell * B + b) * C + c];
-      if (k == d.K - 1) dxo = a.dnll[(size_t)t * B + b] * a.z[((size_t)t * B + b) * C + c] / kLn2;  // d nll / d z = z / ln2
+      if (a.single >= 0) dxo = a.dz_ext[(size_t)b * C + c];
+      else if (k == d.K - 1) dxo = a.dnll[(size_t)t * B + b] * a.z[((size_t)t * B + b) * C + c] / kLn2;  // d nll / d z = z / ln2
       else dxo = a.dx[((cell + Tp) * B + b) * C + c];
     }
     dxr[r * pC + c] = dxo;
@@ -44,7 +45,14 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
     const int r = e / Co, j = e - r * Co;
     orow[r * pO + j] = (r < nrows) ? a.st.o[(cell * B + row0 + r) * Co + j] : 0.f;
   }
-  if (tid < R) dldr[tid] = (tid < nrows) ? -a.dnll[(size_t)t * B + row0 + tid] / kLn2 : 0.f;  // d nll / d logdet
+  if (tid < R) {
+    float v = 0.f;
+    if (tid < nrows) {
+      if (a.single >= 0) v = a.dld_ext ? a.dld_ext[row0 + tid] : 0.f;
+      else v = -a.dnll[(size_t)t * B + row0 + tid] / kLn2;  // d nll / d logdet
+    }
+    dldr[tid] = v;
+  }
   for (int e = tid; e < R * GH; e += NT) {
     const int r = e / GH, j = e - r * GH;
     S[r * pS + j] = (r < nrows) ? a.st.gates[(cell * B + row0 + r) * GH + j] : 0.f;
@@ -57,12 +65,17 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
       if (t > 0) {
         hv = a.st.h[idx - (size_t)B * H];
         if (!gru) cv = a.st.c[idx - (size_t)B * H];
+      } else if (a.single >= 0) {  // module API: the state the cell started from is given
+        const size_t e1 = (size_t)(row0 + r) * H + m;
+        if (a.h_prev_ext) hv = a.h_prev_ext[e1];
+        if (!gru && a.c_prev_ext) cv = a.c_prev_ext[e1];
       }
       if (gru) {
         an = a.st.ahn[idx];
       } else {
         cnv = a.st.c[idx];
-        an = (t < Tp - 1) ? a.dc[idx + (size_t)B * H] : 0.f;  // dc flowing back from cell (k, t+1)
+        if (a.single >= 0) an = a.dc_ext ? a.dc_ext[(size_t)(row0 + r) * H + m] : 0.f;
+        else an = (t < Tp - 1) ? a.dc[idx + (size_t)B * H] : 0.f;  // dc flowing back from cell (k, t+1)
       }
     }
     hp[m * RS + r] = hv;
@@ -115,7 +128,10 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
 
   // ---- E. dh = dlin @ Wf (+ dh from the next frame) ------------------------------------------------
   tile_gemm<RPT>(xs, w.Wf, H, Co, H, sm + sp.wst, [&](int r, int j, float v) {
-    if (r < nrows && t < Tp - 1) v += a.dh[((cell + 1) * B + row0 + r) * H + j];
+    if (r < nrows) {
+      if (a.single >= 0) { if (a.dh_ext) v += a.dh_ext[(size_t)(row0 + r) * H + j]; }
+      else if (t < Tp - 1) v += a.dh[((cell + 1) * B + row0 + r) * H + j];
+    }
     dhr[r * pH + j] = v;
   });
   __syncthreads();
@@ -153,7 +169,8 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
     const int r = e / GH, j = e - r * GH;
     const float vi = S[r * pS + j];
     const float vh = (gru && j >= 2 * H) ? ahn[r * pH + j - 2 * H] : vi;
-    a.dG[((size_t)t * B + row0 + r) * ((size_t)d.K * GH) + (size_t)k * GH + j] = vi;
+    const size_t gld = a.dg_ld ? (size_t)a.dg_ld : (size_t)d.K * GH;
+    a.dG[((size_t)t * B + row0 + r) * gld + (size_t)(k - a.dg_k0) * GH + j] = vi;
     a.dAh[(cell * B + row0 + r) * GH + j] = vh;
   }
   for (int j = tid; j < GH; j += NT) {
@@ -170,6 +187,11 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
       const int r = e / H, j = e - r * H;
       a.dc[(cell * B + row0 + r) * H + j] = ahn[r * pH + j];
     }
+  if (!gru && a.single >= 0 && a.dc0_out)
+    for (int e = tid; e < nrows * H; e += NT) {
+      const int r = e / H, j = e - r * H;
+      a.dc0_out[(size_t)(row0 + r) * H + j] = ahn[r * pH + j];
+    }
 
   // ---- I. dh_prev += dA_h @ W_hh ;  J. dz1 += dA_i @ W_ih[:, :Ci] ----------------------------------
   tile_gemm<RPT>(dact, w.Whh, H, GH, H, sm + sp.wst, [&](int r, int j, float v) { dhr[r * pH + j] += v; },
@@ -180,6 +202,11 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
     for (int e = tid; e < nrows * H; e += NT) {
       const int r = e / H, j = e - r * H;
       a.dh[(cell * B + row0 + r) * H + j] = dhr[r * pH + j];
+    }
+  if (a.single >= 0 && a.dh0_out)
+    for (int e = tid; e < nrows * H; e += NT) {
+      const int r = e / H, j = e - r * H;
+      a.dh0_out[(size_t)(row0 + r) * H + j] = dhr[r * pH + j];
     }
   for (int e = tid; e < R * C; e += NT) {
     const int r = e / C, c = e - r * C;
@@ -195,7 +222,13 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
     prod[r * pO + j] = dy * y;
   });
   __syncthreads();
-  if (k > 0)
+  if (a.single >= 0) {
+    if (a.dx0_out)
+      for (int e = tid; e < nrows * C; e += NT) {
+        const int r = e / C, c = e - r * C;
+        a.dx0_out[(size_t)(row0 + r) * C + c] = dxr[r * pC + c];
+      }
+  } else if (k > 0)
     for (int e = tid; e < nrows * C; e += NT) {
       const int r = e / C, c = e - r * C;
       a.dx[(cell * B + row0 + r) * C + c] = dxr[r * pC + c];
@@ -220,6 +253,28 @@ template <int RPT> static int launch_bwd_t(const BwdArgs &a, cudaStream_t st) {
   }
   LFI_LAUNCH_CHECK_N(a.Tp + K - 1);
   return LFI_OK;
+}
+
+template <int RPT> static int launch_bwd_single_t(const BwdArgs &a, cudaStream_t st) {
+  constexpr int R = Tile<RPT>::R;
+  const int bytes = plan_smem(a.d, R, true, false).total * (int)sizeof(float);
+  LFI_CUDA(cudaFuncSetAttribute(core_bwd_wave<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  core_bwd_wave<RPT><<<dim3((a.B + R - 1) / R, 1), NT, bytes, st>>>(a, a.single, a.single);  // wave = k: t = 0
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
+int launch_bwd_single(const BwdArgs &a, cudaStream_t st) {
+  LFI_REQUIRE(a.single >= 0 && a.single < a.d.K && a.Tp == 1 && a.dz_ext, LFI_ERR_ARG, "flow core backward (single cell): bad arguments");
+  const int rpt = choose_rpt(a.d, a.B, true, false);
+  switch (rpt) {
+    case 8: return launch_bwd_single_t<8>(a, st);
+    case 4: return launch_bwd_single_t<4>(a, st);
+    case 2: return launch_bwd_single_t<2>(a, st);
+    case 1: return launch_bwd_single_t<1>(a, st);
+  }
+  set_error("flow core backward: shape does not fit shared memory (H=%d G=%d C=%d)", a.d.H, a.d.G, a.d.C);
+  return LFI_ERR_SHAPE;
 }
 
 int launch_bwd(const BwdArgs &a, cudaStream_t st) {

@@ -512,6 +512,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
   // 1. sequential core, reverse wavefronts
   core::BwdArgs a;
   memset(&a, 0, sizeof(a));
+  a.single = -1;
   a.d = d; a.dv = make_view(d, derived, p); a.B = B; a.Tp = Tp; a.dnll = dnll; a.z = z; a.st = w.st;
   a.dx = w.dx; a.dh = w.dh; a.dc = w.dc; a.dG = w.dG; a.dAh = w.dAh; a.dO = w.dO; a.dzf = w.dzf;
   a.g_an_bias = g->an_bias; a.g_an_logs = g->an_logs; a.g_b_hh = g->b_hh; a.g_bf = g->bf; a.g_lf = g->lf;
@@ -1086,6 +1087,147 @@ int lfi_gemm(int mode, int transA, int transB, int M, int N, int Kd, const float
   g.sA = strideA; g.sB = strideB; g.sC = strideC; g.sBias = strideBias; g.aux = auxm; g.ldaux = ldaux; g.sAux = strideAux;
   g.batch = batch;
   return gemm_dispatch(mode, g, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// FlowStep.forward with autograd (module API): forward with a stash, and the backward of one cell.
+namespace lfi {
+struct StepStash {  // caller-owned, opaque: activations of one FlowStep.forward call on [B] rows
+  float *Cact, *y, *zf, *h, *c, *gates, *ahn, *o;
+  size_t bytes;
+};
+static void plan_step_stash(const Dims &d, int B, void *base, StepStash *s) {
+  Bump b(base, 0);
+  s->Cact = b.take<float>((size_t)B * d.D);
+  s->y = b.take<float>((size_t)B * d.C);
+  s->zf = b.take<float>((size_t)B * d.C);
+  s->h = b.take<float>((size_t)B * d.H);
+  s->c = b.take<float>((size_t)B * d.H);
+  s->gates = b.take<float>((size_t)B * d.GH);
+  s->ahn = b.take<float>((size_t)B * d.H);
+  s->o = b.take<float>((size_t)B * d.Co);
+  s->bytes = round_up_sz(b.off, 256);
+}
+}  // namespace lfi
+
+extern "C" {
+
+size_t lfi_flowstep_stash_bytes(const lfi_shape *s, int B) {
+  Dims d;
+  if (make_dims(s, &d) != LFI_OK || B < 1) return 0;
+  StepStash q;
+  plan_step_stash(d, B, nullptr, &q);
+  return q.bytes;
+}
+
+size_t lfi_flowstep_bwd_ws_bytes(const lfi_shape *s, int B) {
+  Dims d;
+  if (make_dims(s, &d) != LFI_OK || B < 1) return 0;
+  Bump b(nullptr, 0);
+  b.take<float>((size_t)B * d.GH);  // dG
+  b.take<float>((size_t)B * d.GH);  // dAh
+  b.take<float>((size_t)B * d.Co);  // dO
+  b.take<float>((size_t)B * d.C);   // dzf
+  b.take<float>((size_t)B * d.D);   // dCact
+  return round_up_sz(b.off, 256) + 256;
+}
+
+int lfi_flowstep_fwd_train(const lfi_shape *s, const void *derived, const lfi_params *p, int k, const float *x, const float *cond,
+                           const float *h_in, const float *c_in, float *h_out, float *c_out, float *y, float *logdet,
+                           float *scale_out, int B, void *stash, size_t stash_bytes, void *ws, size_t ws_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d;
+  LFI_TRY(make_dims(s, &d));
+  LFI_REQUIRE(derived && p && x && cond && h_out && y && logdet && ws && stash, LFI_ERR_ARG, "lfi_flowstep_fwd_train: null argument");
+  LFI_REQUIRE(k >= 0 && k < d.K && B >= 1, LFI_ERR_ARG, "lfi_flowstep_fwd_train: bad step %d / batch %d", k, B);
+  LFI_REQUIRE(d.G == 3 || c_out, LFI_ERR_ARG, "lfi_flowstep_fwd_train: LSTM needs c_out");
+  StepStash q;
+  plan_step_stash(d, B, stash, &q);
+  LFI_REQUIRE(stash_bytes >= q.bytes, LFI_ERR_WORKSPACE, "flowstep stash too small: %zu < %zu", stash_bytes, q.bytes);
+  LFI_REQUIRE(ws_bytes >= lfi_flowstep_ws_bytes(s, B), LFI_ERR_WORKSPACE, "flowstep workspace too small");
+  Bump b(ws, ws_bytes);
+  b.take<float>((size_t)B * d.D);
+  float *G = b.take<float>((size_t)B * d.GH);
+  float *xin = b.take<float>((size_t)B * d.C * 2);
+  void *gws = (char *)ws + round_up_sz(b.off, 256);
+  const size_t gws_bytes = ws_bytes - round_up_sz(b.off, 256);
+  const int In = d.Ci + d.D;
+  GemmArgs g1 = gemm_args(0, 1, B, d.D, d.F, cond, d.F, p->wc + (size_t)k * d.D * d.F, d.F, q.Cact, d.D, LFI_EPI_BIAS | LFI_EPI_LRELU,
+                          p->bc + (size_t)k * d.D);
+  LFI_TRY(gemm_dispatch(LFI_GEMM_FP32, g1, gws, gws_bytes, st));
+  GemmArgs g2 = gemm_args(0, 1, B, d.GH, d.D, q.Cact, d.D, p->w_ih + (size_t)k * d.GH * In + d.Ci, In, G, d.GH, LFI_EPI_BIAS,
+                          p->b_ih + (size_t)k * d.GH);
+  LFI_TRY(gemm_dispatch(LFI_GEMM_FP32, g2, gws, gws_bytes, st));
+  const size_t kB = (size_t)k * B;
+  core::FwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = d; a.dv = make_view(d, derived, p); a.B = B; a.Tp = 1; a.k_first = k; a.k_last = k;
+  a.x0 = x; a.x_sb = d.C; a.x_st = 0; a.G = G; a.g_ld = d.GH; a.g_k0 = k;
+  a.h0 = h_in ? h_in - kB * d.H : nullptr; a.c0 = c_in ? c_in - kB * d.H : nullptr;
+  a.xin = xin - kB * d.C;
+  // the stash arrays are [K][Tp][B][width]: moved back by k cells so that cell (k, 0) lands on the caller's buffers
+  a.st_y = q.y - kB * d.C; a.st_zf = q.zf - kB * d.C; a.st_h = q.h - kB * d.H; a.st_c = d.G == 4 ? q.c - kB * d.H : nullptr;
+  a.st_gates = q.gates - kB * d.GH; a.st_ahn = d.G == 3 ? q.ahn - kB * d.H : nullptr; a.st_o = q.o - kB * d.Co;
+  a.ld = logdet; a.ld_accumulate = 1; a.nll = nullptr; a.z_out = y;
+  a.scale_out = scale_out ? scale_out - kB * d.Cz : nullptr;
+  LFI_TRY(core::launch_fwd(a, st));
+  LFI_CUDA(cudaMemcpyAsync(h_out, q.h, (size_t)B * d.H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (d.G == 4) LFI_CUDA(cudaMemcpyAsync(c_out, q.c, (size_t)B * d.H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return LFI_OK;
+}
+
+int lfi_flowstep_bwd(const lfi_shape *s, const void *derived, const lfi_params *p, int k, const float *cond, const float *h_in,
+                     const float *c_in, const float *dy, const float *dlogdet, const float *dh_out, const float *dc_out, float *dx,
+                     float *dcond, float *dh_in, float *dc_in, lfi_params *g, int B, void *stash, size_t stash_bytes, void *ws,
+                     size_t ws_bytes, void *stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d;
+  LFI_TRY(make_dims(s, &d));
+  LFI_REQUIRE(derived && p && cond && dy && dx && dcond && dh_in && g && stash && ws, LFI_ERR_ARG, "lfi_flowstep_bwd: null argument");
+  LFI_REQUIRE(k >= 0 && k < d.K && B >= 1, LFI_ERR_ARG, "lfi_flowstep_bwd: bad step %d / batch %d", k, B);
+  LFI_REQUIRE(d.G == 3 || dc_in, LFI_ERR_ARG, "lfi_flowstep_bwd: LSTM needs dc_in");
+  StepStash q;
+  plan_step_stash(d, B, stash, &q);
+  LFI_REQUIRE(stash_bytes >= q.bytes, LFI_ERR_WORKSPACE, "flowstep stash too small");
+  LFI_REQUIRE(ws_bytes >= lfi_flowstep_bwd_ws_bytes(s, B), LFI_ERR_WORKSPACE, "flowstep backward workspace too small");
+  Bump b(ws, ws_bytes);
+  float *dG = b.take<float>((size_t)B * d.GH), *dAh = b.take<float>((size_t)B * d.GH), *dO = b.take<float>((size_t)B * d.Co);
+  float *dzf = b.take<float>((size_t)B * d.C), *dC = b.take<float>((size_t)B * d.D);
+  const int C = d.C, Ci = d.Ci, GH = d.GH, H = d.H, D = d.D, Co = d.Co, In = Ci + D, F = d.F;
+  const size_t kB = (size_t)k * B;
+  core::BwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.d = d; a.dv = make_view(d, derived, p); a.B = B; a.Tp = 1; a.single = k;
+  a.st.y = q.y - kB * C; a.st.zf = q.zf - kB * C; a.st.h = q.h - kB * H; a.st.c = d.G == 4 ? q.c - kB * H : nullptr;
+  a.st.gates = q.gates - kB * GH; a.st.ahn = d.G == 3 ? q.ahn - kB * H : nullptr; a.st.o = q.o - kB * Co;
+  a.dz_ext = dy; a.dld_ext = dlogdet; a.dh_ext = dh_out; a.dc_ext = dc_out; a.h_prev_ext = h_in; a.c_prev_ext = c_in;
+  a.dx0_out = dx; a.dh0_out = dh_in; a.dc0_out = dc_in;
+  a.dG = dG; a.dg_ld = GH; a.dg_k0 = k;
+  a.dAh = dAh - kB * GH; a.dO = dO - kB * Co; a.dzf = dzf - kB * C;
+  a.g_an_bias = g->an_bias; a.g_an_logs = g->an_logs; a.g_b_hh = g->b_hh; a.g_bf = g->bf; a.g_lf = g->lf;
+  LFI_TRY(core::launch_bwd_single(a, st));
+  // weight gradients of this cell (fp32 tiles): reductions over the B rows
+  auto wg = [&](int Mo, int No, const float *A, int lda, const float *Bm, int ldb, float *Cm, int ldc) -> int {
+    GemmArgs r = gemm_args(1, 0, Mo, No, B, A, lda, Bm, ldb, Cm, ldc, LFI_EPI_ACCUM);
+    return gemm_simt(r, st);
+  };
+  if (h_in) LFI_TRY(wg(GH, H, dAh, GH, h_in, H, g->w_hh + (size_t)k * GH * H, H));
+  LFI_TRY(wg(GH, Ci, dG, GH, q.zf, C, g->w_ih + (size_t)k * GH * In, In));
+  LFI_TRY(wg(GH, D, dG, GH, q.Cact, D, g->w_ih + (size_t)k * GH * In + Ci, In));
+  LFI_TRY(wg(Co, H, dO, Co, q.h, H, g->wf + (size_t)k * Co * H, H));
+  LFI_TRY(wg(C, C, q.y, C, dzf, C, g->w + (size_t)k * C * C, C));
+  LFI_TRY(aux::colsum(g->b_ih + (size_t)k * GH, dG, GH, B, GH, 1.0f, st));
+  // cond_transform backward: dC = (dG W_ih[:, Ci:]) * LeakyReLU'(Cact); d b_c, d W_c, d cond
+  GemmArgs t = gemm_args(0, 0, B, D, GH, dG, GH, p->w_ih + (size_t)k * GH * In + Ci, In, dC, D, LFI_EPI_LRELU_BWD);
+  t.aux = q.Cact; t.ldaux = D;
+  LFI_TRY(gemm_simt(t, st));
+  LFI_TRY(aux::colsum(g->bc + (size_t)k * D, dC, D, B, D, 1.0f, st));
+  LFI_TRY(wg(D, F, dC, D, cond, F, g->wc + (size_t)k * D * F, F));
+  GemmArgs u = gemm_args(0, 0, B, F, D, dC, D, p->wc + (size_t)k * D * F, F, dcond, F, 0);
+  LFI_TRY(gemm_simt(u, st));
+  return LFI_OK;
 }
 
 }  // extern "C"

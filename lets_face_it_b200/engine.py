@@ -450,3 +450,89 @@ class Engine:
             const = self.step_logdet_const(k)
             logdet = logdet + (ld - const if reverse else ld + const)
         return y, logdet, h_out, c_out, scale
+
+    # ------------------------------------------------------------------ FlowStep.forward under autograd
+    _STEP_GRAD_BLOCKS = ("an_bias", "an_logs", "w", "wc", "bc", "w_ih", "b_ih", "w_hh", "b_hh", "wf", "bf", "lf")
+
+    def _step_block_numel(self):
+        C, D, F, GH, H, Co, In = self.C, self.D, self.F, self.G * self.H, self.H, self.Co, self.Ci + self.D
+        return {"an_bias": C, "an_logs": C, "w": C * C, "wc": D * F, "bc": D, "w_ih": GH * In, "b_ih": GH, "w_hh": GH * H, "b_hh": GH,
+                "wf": Co * H, "bf": Co, "lf": Co}
+
+    @_on_own_device
+    def flowstep_train(self, k, x, cond, h_in, c_in, want_scale=False):
+        """Forward of one FlowStep on one frame WITH the stash `flowstep_backward` needs (lfi_flowstep_fwd_train).
+        Returns (y, ld [B] coupling log-det term, h_out, c_out, scale, stash)."""
+        self.refresh(False)
+        L, st = cabi.lib(), cabi.stream_ptr()
+        P = self._params_struct(self.theta, self.W)
+        dev = self.theta.device
+        x = x.detach().to(device=dev, dtype=torch.float32).contiguous()
+        cond = cond.detach().to(device=dev, dtype=torch.float32).contiguous()
+        h_in = h_in.detach().to(device=dev, dtype=torch.float32).contiguous() if h_in is not None else None
+        c_in = c_in.detach().to(device=dev, dtype=torch.float32).contiguous() if c_in is not None else None
+        B = x.shape[0]
+        if x.shape[1] != self.C or cond.shape[1] != self.F:
+            raise RuntimeError("flow step expects x [B,%d] and cond [B,%d], got %s / %s" % (self.C, self.F, tuple(x.shape), tuple(cond.shape)))
+        y = torch.empty_like(x)
+        h_out = torch.empty(B, self.H, dtype=torch.float32, device=dev)
+        c_out = torch.empty(B, self.H, dtype=torch.float32, device=dev) if self.G == 4 else None
+        ld = torch.zeros(B, dtype=torch.float32, device=dev)
+        scale = torch.empty(B, self.Cz, dtype=torch.float32, device=dev) if (want_scale and self.affine) else None
+        stash = torch.empty(L.lfi_flowstep_stash_bytes(ctypes.byref(self.shape), B), dtype=torch.uint8, device=dev)
+        ws = self._workspace(("step", B), L.lfi_flowstep_ws_bytes(ctypes.byref(self.shape), B))
+        cabi.check(L.lfi_flowstep_fwd_train(ctypes.byref(self.shape), self._derived.data_ptr(), ctypes.byref(P), k, x.data_ptr(), cond.data_ptr(),
+                                            cabi.ptr(h_in), cabi.ptr(c_in), h_out.data_ptr(), c_out.data_ptr() if c_out is not None else None,
+                                            y.data_ptr(), ld.data_ptr(), scale.data_ptr() if scale is not None else None, B,
+                                            stash.data_ptr(), stash.numel(), ws.data_ptr(), ws.numel(), st), "lfi_flowstep_fwd_train")
+        return y, ld, h_out, c_out, scale, (stash, cond, h_in, c_in)
+
+    @_on_own_device
+    def flowstep_backward(self, k, saved, dy, dld, dh_out, dc_out):
+        """Backward of `flowstep_train` (lfi_flowstep_bwd).  Returns (dx, dcond, dh_in, dc_in, grads) with grads a dict
+        block name -> gradient tensor of step k's block (dW of the composed 1x1 weight under "w")."""
+        L, st = cabi.lib(), cabi.stream_ptr()
+        stash, cond, h_in, c_in = saved
+        dev = self.theta.device
+        P = self._params_struct(self.theta, self.W)
+        B = cond.shape[0]
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous() if t is not None else None
+        dy = f32(dy) if dy is not None else torch.zeros(B, self.C, device=dev)
+        dld, dh_out, dc_out = f32(dld), f32(dh_out), f32(dc_out)
+        dx = torch.empty(B, self.C, dtype=torch.float32, device=dev)
+        dcond = torch.empty(B, self.F, dtype=torch.float32, device=dev)
+        dh_in = torch.empty(B, self.H, dtype=torch.float32, device=dev)
+        dc_in = torch.empty(B, self.H, dtype=torch.float32, device=dev) if self.G == 4 else None
+        numel = self._step_block_numel()
+        offs, o = {}, 0
+        for n in self._STEP_GRAD_BLOCKS:
+            offs[n] = o
+            o = _align(o + numel[n])
+        gbuf = torch.zeros(o, dtype=torch.float32, device=dev)
+        G = cabi.Params()
+        for n in self._STEP_GRAD_BLOCKS:  # the C side indexes [K, ...] blocks: base moved back by k blocks
+            setattr(G, n, gbuf.data_ptr() + 4 * offs[n] - 4 * k * numel[n])
+        ws = self._workspace(("stepbwd", B), L.lfi_flowstep_bwd_ws_bytes(ctypes.byref(self.shape), B))
+        cabi.check(L.lfi_flowstep_bwd(ctypes.byref(self.shape), self._derived.data_ptr(), ctypes.byref(P), k, cond.data_ptr(), cabi.ptr(h_in),
+                                      cabi.ptr(c_in), dy.data_ptr(), cabi.ptr(dld), cabi.ptr(dh_out), cabi.ptr(dc_out), dx.data_ptr(),
+                                      dcond.data_ptr(), dh_in.data_ptr(), dc_in.data_ptr() if dc_in is not None else None, ctypes.byref(G), B,
+                                      stash.data_ptr(), stash.numel(), ws.data_ptr(), ws.numel(), st), "lfi_flowstep_bwd")
+        grads = {n: gbuf[offs[n]:offs[n] + numel[n]] for n in self._STEP_GRAD_BLOCKS}
+        return dx, dcond, dh_in, dc_in, grads
+
+    @_on_own_device
+    def invconv_chain_rule(self, k, dW):
+        """dL/d(l, u, log_s) of step k from dL/dW of its composed weight (lfi_invconv_compose_bwd on one step)."""
+        L, st = cabi.lib(), cabi.stream_ptr()
+        C, dev = self.C, self.theta.device
+        n = C * C
+        blk = lambda name, m: self.block(name)[k * m:(k + 1) * m]
+        dl = torch.zeros(C, C, device=dev)
+        du = torch.zeros(C, C, device=dev)
+        dls = torch.zeros(C, device=dev)
+        ws = self._workspace(("invconv1",), L.lfi_invconv_ws_bytes(1, C))
+        cabi.check(L.lfi_invconv_compose_bwd(1, C, self.perm[k].contiguous().data_ptr(), blk("inv_l", n).data_ptr(), blk("inv_u", n).data_ptr(),
+                                             blk("inv_log_s", C).data_ptr(), self.sign_s[k].contiguous().data_ptr(), dW.contiguous().data_ptr(),
+                                             dl.data_ptr(), du.data_ptr(), dls.data_ptr(), ws.data_ptr(), ws.numel(), st),
+                   "lfi_invconv_compose_bwd")
+        return dl, du, dls

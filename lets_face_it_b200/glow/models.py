@@ -233,6 +233,43 @@ class f_seq(nn.Module):
         raise NotImplementedError("f_seq is evaluated inside the fused FlowStep kernel (call FlowStep.forward)")
 
 
+class _FlowStepFn(torch.autograd.Function):
+    """One FlowStep on one frame under autograd (reference: FlowStep.normal_flow, models.py:311-342, differentiated by
+    torch): forward = lfi_flowstep_fwd_train, backward = lfi_flowstep_bwd + the LU chain rule.  Inputs after `c_in` are the
+    step's parameters in `FlowStep._autograd_params()` order (graph connectivity; values are read from the flat buffer)."""
+
+    @staticmethod
+    def forward(ctx, eng, k, want_scale, n_lu, x, cond, h_in, c_in, *params):
+        y, ld, h_out, c_out, scale, saved = eng.flowstep_train(k, x, cond, h_in, c_in, want_scale)
+        ctx.eng, ctx.k, ctx.saved, ctx.n_lu = eng, k, saved, n_lu
+        ctx.has_c = c_out is not None
+        outs = (y, ld, h_out) + ((c_out,) if c_out is not None else ()) + ((scale,) if scale is not None else ())
+        if scale is not None:
+            ctx.mark_non_differentiable(scale)
+        ctx.n_out = len(outs)
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        eng, k = ctx.eng, ctx.k
+        dy, dld, dh_out = grads[0], grads[1], grads[2]
+        dc_out = grads[3] if ctx.has_c else None
+        dx, dcond, dh_in, dc_in, g = eng.flowstep_backward(k, ctx.saved, dy, dld, dh_out, dc_out)
+        C = eng.C
+        out = [g["an_bias"].view(1, C), g["an_logs"].view(1, C)]
+        if ctx.n_lu:
+            dl, du, dls = eng.invconv_chain_rule(k, g["w"])
+            out += [dl, du, dls]
+        else:
+            out += [g["w"].view(C, C)]
+        GH, In, H, D, F, Co = eng.G * eng.H, eng.Ci + eng.D, eng.H, eng.D, eng.F, eng.Co
+        out += [g["wc"].view(D, F), g["bc"], g["w_ih"].view(GH, In), g["b_ih"], g["w_hh"].view(GH, H), g["b_hh"],
+                g["wf"].view(Co, H), g["bf"], g["lf"]]
+        _, h_in, c_in = ctx.saved[1], ctx.saved[2], ctx.saved[3]
+        return (None, None, None, None, dx, dcond, dh_in if h_in is not None else None,
+                dc_in if (c_in is not None and dc_in is not None) else None) + tuple(out)
+
+
 class FlowStep(nn.Module):
     """ActNorm -> invertible 1x1 conv -> affine/additive coupling (reference models.py:217-376)."""
 
@@ -269,12 +306,45 @@ class FlowStep(nn.Module):
             Engine([self], None)  # registers itself on the step
         return self._engine
 
+    def _autograd_params(self):
+        inv = [self.invconv.l, self.invconv.u, self.invconv.log_s] if self.invconv.LU else [self.invconv.weight]
+        f = self.f
+        return [self.actnorm.bias, self.actnorm.logs] + inv + [f.cond_transform[0].weight, f.cond_transform[0].bias, f.rnn.weight_ih, f.rnn.bias_ih,
+                                                              f.rnn.weight_hh, f.rnn.bias_hh, f.final_linear.weight, f.final_linear.bias,
+                                                              f.final_linear.logs]
+
+    def _forward_autograd(self, eng, input_, cond, logdet):
+        """normal_flow under autograd: kernels for everything data dependent, torch for the parameter-only log-det terms
+        C * sum(logs) + C * sum(log_s) (modules.py:62, 171) so that autograd owns their gradients."""
+        params = self._autograd_params()
+        h_in, c_in = self.f.hidden, self.f.cell
+        outs = _FlowStepFn.apply(eng, self._k, bool(self.scale_logging), 1 if self.invconv.LU else 0, input_, cond, h_in, c_in, *params)
+        y, ld, h = outs[0], outs[1], outs[2]
+        i = 3
+        c = None
+        if eng.G == 4:
+            c = outs[i]
+            i += 1
+        if self.scale_logging and eng.affine:
+            self.scale = outs[i]
+        self.f.hidden, self.f.cell = h, c
+        C = float(eng.C)
+        const = self.actnorm.logs.sum() * C
+        const = const + (self.invconv.log_s.sum() * C if self.invconv.LU else torch.slogdet(self.invconv.weight)[1] * C)
+        if logdet is not None:
+            logdet = logdet + ld + const
+        return y, logdet
+
     def forward(self, input_, audio_features, logdet=None, reverse=False, _refresh=True):
         assert audio_features is not None
         eng = self._eng()
         eng.ensure(input_.device if input_.is_cuda else None)
         if not reverse and not self.actnorm.inited:
             self.actnorm.initialize_parameters(input_)
+        if not reverse and torch.is_grad_enabled() and (
+                input_.requires_grad or audio_features.requires_grad or any(p.requires_grad for p in self._autograd_params())
+                or (self.f.hidden is not None and self.f.hidden.requires_grad)):
+            return self._forward_autograd(eng, input_, audio_features, logdet)
         y, logdet, h, c, scale = eng.flowstep(self._k, input_, audio_features, self.f.hidden, self.f.cell, logdet, bool(reverse),
                                               want_scale=self.scale_logging, refresh=_refresh)
         self.f.hidden, self.f.cell = h, c

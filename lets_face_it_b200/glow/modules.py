@@ -3,8 +3,9 @@
 Same class names, constructor signatures, parameter/buffer names and shapes as
 `code/glow_pytorch/glow/modules.py` of the reference (so its checkpoints load), but
 `forward` calls liblfi_b200.so through `_cabi` — CUDA tensors only, no torch fallback.
-Stand-alone use of these primitives (as in the reference's test_modules.py) is inference-style:
-gradients flow through the fused `SeqGlow.forward` path (models.py), not through these calls.
+Gradients flow through the fused `SeqGlow.forward` path and through `FlowStep / FlowNet / Glow.forward` (one autograd node
+per flow step and frame, models.py: `_FlowStepFn`); the stand-alone `ActNorm2d / InvertibleConv1x1 / LinearZeros` calls below
+(the reference's test_modules.py:9-27 round trips) are inference-style.
 """
 from __future__ import annotations
 
