@@ -196,6 +196,11 @@ int lfi_nll(const float *z, const float *logdet, float *nll, int B, int C, void 
 int lfi_expand_faces(const float *x, const float *means, const float *stds, size_t rows, int exp_dim, int jaw_dim, int neck_dim,
                      float *out, void *stream);
 
+/* Validation metric on the device: calc_jerk of glow/utils.py:53-58 (mimicry_logger.py:175-184),
+ * the mean absolute third difference along time of x [B, T, C] (T >= 4).  scratch8: 8 bytes, 8-byte aligned; out: one float.
+ * Differences are three rounded fp32 subtractions as in torch; the mean is accumulated in fp64. */
+int lfi_jerk(const float *x, int B, int T, int C, void *scratch8, float *out, void *stream);
+
 /* fused gradient-norm clip + Adam over the flat parameter buffer (lets_face_it_glow.py:61-72,
  * final_model.yaml:126,130): two launches, no host sync.  norm_scratch: 2 floats. */
 int lfi_clip_adam(float *theta, float *grad, float *m, float *v, size_t n, float lr, float beta1, float beta2,

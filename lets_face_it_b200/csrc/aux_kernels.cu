@@ -722,5 +722,41 @@ int expand_faces(const float *x, const float *means, const float *stds, size_t r
   return LFI_OK;
 }
 
+// Validation metric of the reference (calc_jerk, glow/utils.py:53-58; mimicry_logger.py:175-184): mean |third difference| along
+// time of [B, T, C].  The three differences are taken as three rounded fp32 subtractions, exactly as torch does; the sum runs
+// in fp64 (per-block partial sums, one atomic per block), so the mean agrees with the reference's to fp32 rounding.
+__global__ void jerk_kernel(const float *__restrict__ x, int B, int T, int C, double *__restrict__ acc) {
+  const size_t n = (size_t)B * (T - 3) * C;
+  double s = 0.0;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const size_t q = e / C;
+    const int t = (int)(q % (T - 3)), b = (int)(q / (T - 3));
+    const float *p = x + ((size_t)b * T + t) * C + c;
+    const float x0 = p[0], x1 = p[C], x2 = p[2 * (size_t)C], x3 = p[3 * (size_t)C];
+    const float d0 = __fsub_rn(x1, x0), d1 = __fsub_rn(x2, x1), d2 = __fsub_rn(x3, x2);
+    const float a0 = __fsub_rn(d1, d0), a1 = __fsub_rn(d2, d1);
+    s += (double)fabsf(__fsub_rn(a1, a0));
+  }
+  __shared__ double red[TB / 32];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < TB / 32; ++i) t += red[i];
+    atomicAdd(acc, t);
+  }
+}
+__global__ void jerk_finish_kernel(const double *acc, double n, float *out) { out[0] = (float)(acc[0] / n); }
+int jerk(const float *x, int B, int T, int C, double *scratch, float *out, cudaStream_t st) {
+  LFI_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), st));
+  const size_t n = (size_t)B * (T - 3) * C;
+  jerk_kernel<<<blocks_for(n), TB, 0, st>>>(x, B, T, C, scratch);
+  jerk_finish_kernel<<<1, 1, 0, st>>>(scratch, (double)n, out);
+  LFI_LAUNCH_CHECK_N(2);
+  return LFI_OK;
+}
+
 }  // namespace aux
 }  // namespace lfi

@@ -92,5 +92,7 @@ int colsum_planes(float *out1, float *out2, int period, int lim2, long so, const
                   int col0, int cols, cudaStream_t st);
 int expand_faces(const float *x, const float *means, const float *stds, size_t rows, int exp_dim, int jaw_dim, int neck_dim, float *out,
                  cudaStream_t st);
+// calc_jerk (glow/utils.py:53-58): mean |third time difference| of x [B, T, C]; scratch: one double; out: one float
+int jerk(const float *x, int B, int T, int C, double *scratch, float *out, cudaStream_t st);
 }  // namespace aux
 }  // namespace lfi

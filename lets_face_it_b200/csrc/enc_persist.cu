@@ -41,6 +41,10 @@ constexpr int kThreads = 32 * (kEpiWarps + 2);  // + TMA producer warp + MMA iss
 constexpr int kKB = 64;               // bf16 elements per k-block (one 128-byte swizzle span)
 constexpr int kAKB = kRows * 128;     // bytes of one k-block of one A plane
 constexpr int kTmemCols = 512;
+// The gate phase is issue-latency bound (ncu: 2 gate warps per scheduler sustain ~0.3 instructions per cycle): the forward kernel
+// runs 16 gate warps (4 per scheduler, 96 registers each) instead of 8.
+constexpr int kFwdGateWarps = 8;
+constexpr int kFwdThreads = 32 * (kFwdGateWarps + 2);
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -58,14 +62,18 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t *bar, uint32_t pa
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
-// bounded wait with cluster-scope acquire (the arrivals come from both CTAs of the cluster)
+// bounded wait on a barrier whose arrivals come from both CTAs of the cluster (mbarrier.arrive.release.cluster).  The wait
+// itself uses the default (CTA-scope) acquire: the data it guards lives in THIS CTA's shared memory (written by the peer
+// through DSMEM before its release-arrive), and a cluster-scope acquire makes the compiler invalidate L1 (CCTL.IVALL) on every
+// spin iteration - 21 % of the stall samples of the first version (profiles/r02_enc_persist_ncu.txt).  Same pattern as the
+// CTA-pair GEMM (gemm_tc.cu) and CUTLASS' ClusterBarrier::wait.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   unsigned long long t0;
@@ -93,24 +101,6 @@ __device__ __forceinline__ void unpack8(const uint4 &hi, const uint4 &lo, float 
   v[4] = bf_lo(hi.z) + bf_lo(lo.z); v[5] = bf_hi(hi.z) + bf_hi(lo.z);
   v[6] = bf_lo(hi.w) + bf_lo(lo.w); v[7] = bf_hi(hi.w) + bf_hi(lo.w);
 }
-__device__ __forceinline__ void ld16(const float *p, float *v) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 t = *reinterpret_cast<const float4 *>(p + 4 * i);
-    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-  }
-}
-__device__ __forceinline__ void ldg16(const float *p, float *v) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 t = __ldg(reinterpret_cast<const float4 *>(p + 4 * i));
-    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-  }
-}
-__device__ __forceinline__ void st16(float *p, const float *v) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4 *>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-}
 __device__ __forceinline__ uint32_t pack_u16(unsigned short a, unsigned short b) { return (uint32_t)a | ((uint32_t)b << 16); }
 
 constexpr int kStageBytes = 192 * 128;  // forward ring stage: one 64-unit half (r, u, n rows) of one k-block of one W_hh plane
@@ -134,18 +124,47 @@ __host__ __device__ inline SmemPlan plan(int E) {
 }
 
 // 16 consecutive columns n0 .. n0+15 of row `row` of a tiled fp32 array of width W (enc_persist.cuh)
-__device__ __forceinline__ void ldt16(const float *base, size_t row, int n0, int W, float *v) {
-  const float *p = base + ((row >> 5) * (size_t)(W >> 2) + (size_t)(n0 >> 2)) * 128 + (row & 31) * 4;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 t = *reinterpret_cast<const float4 *>(p + i * 128);
-    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-  }
+// 8-column variants (two 4-column groups)
+// L1 policy: with 225 KB of shared memory per CTA the L1 is a few tens of KB.  The streams (input projections, stash) pass it
+// without allocating; the bias vectors, which every chunk of every step re-reads, are asked to stay (evict-last).
+__device__ __forceinline__ float4 ld_stream4(const float *p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
 }
-__device__ __forceinline__ void stt16(float *base, size_t row, int n0, int W, const float *v) {
+__device__ __forceinline__ float4 ld_keep4(const float *p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream4(float *p, float a, float b, float c, float d) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_stream_u4(void *p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void ldt8(const float *base, size_t row, int n0, int W, float *v) {
+  const float *p = base + ((row >> 5) * (size_t)(W >> 2) + (size_t)(n0 >> 2)) * 128 + (row & 31) * 4;
+  const float4 t0 = ld_stream4(p), t1 = ld_stream4(p + 128);
+  v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+}
+__device__ __forceinline__ void stt8(float *base, size_t row, int n0, int W, const float *v) {
   float *p = base + ((row >> 5) * (size_t)(W >> 2) + (size_t)(n0 >> 2)) * 128 + (row & 31) * 4;
+  st_stream4(p, v[0], v[1], v[2], v[3]);
+  st_stream4(p + 128, v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void ldg8(const float *p, float *v) {
+  const float4 t0 = ld_keep4(p), t1 = ld_keep4(p + 4);
+  v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {  // lane = TMEM lane (row), 8 consecutive columns
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
 #pragma unroll
-  for (int i = 0; i < 4; ++i) *reinterpret_cast<float4 *>(p + i * 128) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ unsigned short *u16_ptr(void *base, size_t row, int n0, int W) {
   return reinterpret_cast<unsigned short *>(base) + ((row >> 5) * (size_t)(W >> 3) + (size_t)(n0 >> 3)) * 256 + (row & 31) * 8;
@@ -153,7 +172,7 @@ __device__ __forceinline__ unsigned short *u16_ptr(void *base, size_t row, int n
 
 }  // namespace
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
 enc_gru_fwd_persist(const FwdArgs a, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
   extern __shared__ __align__(16) uint8_t smraw[];
   uint8_t *smb = (uint8_t *)(((uintptr_t)smraw + 1023) & ~(uintptr_t)1023);
@@ -172,10 +191,10 @@ enc_gru_fwd_persist(const FwdArgs a, const __grid_constant__ CUtensorMap map_hi,
     for (int s = 0; s < pl.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(mma_local, 1);
     mbar_init(mma_done, 2);                // this CTA's relay + the peer's
-    mbar_init(a_ready, 2 * kEpiWarps);     // every gate warp of both CTAs
+    mbar_init(a_ready, 2 * kFwdGateWarps);     // every gate warp of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kEpiWarps + 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == kFwdGateWarps + 1) tmem_alloc(tmem_slot, kTmemCols);
   fence_before();
   __syncthreads();
   cluster.sync();  // both CTAs run and their barriers are initialised before any remote access
@@ -184,7 +203,7 @@ enc_gru_fwd_persist(const FwdArgs a, const __grid_constant__ CUtensorMap map_hi,
   const int tile = blockIdx.y;
   const uint32_t my_rank = (uint32_t)c, peer_rank = (uint32_t)(c ^ 1);
 
-  if (warp == kEpiWarps) {
+  if (warp == kFwdGateWarps) {
     // ============================== TMA producer: this CTA's rows of W_hh: k-block, plane, 64-unit half ====================
     if (lane == 0) {
       int st = 0; uint32_t ph = 0;
@@ -201,14 +220,14 @@ enc_gru_fwd_persist(const FwdArgs a, const __grid_constant__ CUtensorMap map_hi,
               if (++st == pl.stages) { st = 0; ph ^= 1; }
             }
     }
-  } else if (warp == kEpiWarps + 1) {
+  } else if (warp == kFwdGateWarps + 1) {
     // ============================== MMA issuer ==============================================================================
     if (lane == 0) {
       const uint32_t sAu = smem_u32(sA), sBu = smem_u32(sB);
       const uint32_t done_own = mapa_u32(smem_u32(mma_done), my_rank), done_peer = mapa_u32(smem_u32(mma_done), peer_rank);
       const uint32_t idesc = idesc_bf16_m128(192);
       int st = 0; uint32_t ph = 0;
-      const bool tm = a.timing && blockIdx.x == 0 && blockIdx.y == 0;
+      const bool tm = (a.timing & 1) && blockIdx.x == 0 && blockIdx.y == 0;
       long long t_wait = 0, t_mma = 0;
       for (int s = 1; s < hist; ++s) {
         const long long c0 = tm ? clock64() : 0;
@@ -251,23 +270,22 @@ enc_gru_fwd_persist(const FwdArgs a, const __grid_constant__ CUtensorMap map_hi,
     const size_t m_raw = (size_t)tile * kRows + L;
     const bool row_ok = m_raw < (size_t)a.M;
     const size_t m = row_ok ? m_raw : (size_t)a.M - 1;  // clamped: rows beyond M compute on valid addresses and store nothing
-    const int UQ = UH >> 1, nch = UQ / 16;
+    const int UQ = UH / (kFwdGateWarps / 4), nch = UQ / 8;      // chunks of 8 units: the working set fits the 168-register budget without spills
     const uint32_t tlane = tmem + ((uint32_t)(32 * q) << 16);
     const uint32_t ready_own = mapa_u32(smem_u32(a_ready), my_rank), ready_peer = mapa_u32(smem_u32(a_ready), peer_rank);
     const bool cond_vec = a.cond && (((uintptr_t)a.cond & 15) == 0) && (a.cond_ld % 4 == 0);
     const size_t Mp = tiled_rows((size_t)a.M);
-    const bool tm = a.timing && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
+    const bool tm = (a.timing & 1) && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0;
     long long t_wait = 0, t_epi = 0;
+    const int ug_first = c * UH + sub * UQ;
     for (int s = 0; s < hist; ++s) {
       const long long c0 = tm ? clock64() : 0;
       const float mk = a.mask ? __ldg(a.mask + m * hist + s) : 1.0f;
       const size_t xr_row = m + (size_t)(a.t0 - hist + 1 + s) * a.B;  // raw frame of this window at this step (time-major rows)
       const bool lastStep = (s == hist - 1);
-      float xr[16], xu[16], xn[16];
-      {  // operands of the first chunk are requested before the wait for the products
-        const int ug0 = c * UH + sub * UQ;
-        ldt16(a.xp, xr_row, ug0, 3 * E, xr); ldt16(a.xp, xr_row, E + ug0, 3 * E, xu); ldt16(a.xp, xr_row, 2 * E + ug0, 3 * E, xn);
-      }
+      float xr[8], xu[8], xn[8];
+      // operands of the first chunk are requested before the wait for the products
+      ldt8(a.xp, xr_row, ug_first, 3 * E, xr); ldt8(a.xp, xr_row, E + ug_first, 3 * E, xu); ldt8(a.xp, xr_row, 2 * E + ug_first, 3 * E, xn);
       if (s > 0) {
         mbar_wait_cluster(mma_done, (uint32_t)((s - 1) & 1));
         fence_after();
@@ -275,100 +293,90 @@ enc_gru_fwd_persist(const FwdArgs a, const __grid_constant__ CUtensorMap map_hi,
       const long long c1 = tm ? clock64() : 0;
       t_wait += c1 - c0;
       for (int j = 0; j < nch; ++j) {
-        const int ul = sub * UQ + 16 * j, ug = c * UH + ul;
-        if (j > 0) { ldt16(a.xp, xr_row, ug, 3 * E, xr); ldt16(a.xp, xr_row, E + ug, 3 * E, xu); ldt16(a.xp, xr_row, 2 * E + ug, 3 * E, xn); }
-        float ar[16], au[16], an[16], hp[16];
-        const uint32_t aoff = (uint32_t)(ug >> 6) * kAKB;       // k-block of these units inside a plane
-        const uint32_t o0 = aoff + sw128_off(L, (ug & 63) >> 3), o1 = aoff + sw128_off(L, ((ug & 63) >> 3) + 1);
+        const int ul = sub * UQ + 8 * j, ug = c * UH + ul;
+        float ar[8], au[8], an[8], hp[8];
+        const uint32_t o0 = (uint32_t)(ug >> 6) * kAKB + sw128_off(L, (ug & 63) >> 3);  // 16-byte piece of these 8 units in a plane
+        float bri[8], brh[8], bui[8], buh[8];  // the r / u biases are requested before the accumulators are read ...
+        ldg8(a.b_ih + ug, bri); ldg8(a.b_hh + ug, brh); ldg8(a.b_ih + E + ug, bui); ldg8(a.b_hh + E + ug, buh);
         if (s > 0) {
           const uint32_t tcol = (uint32_t)((ul >> 6) * 192 + (ul & 63));  // accumulator columns: per 64-unit half [r | u | n]
-          tmem_ld16(tlane + tcol, ar);
-          tmem_ld16(tlane + tcol + 64, au);
-          tmem_ld16(tlane + tcol + 128, an);
+          tmem_ld8(tlane + tcol, ar);
+          tmem_ld8(tlane + tcol + 64, au);
+          tmem_ld8(tlane + tcol + 128, an);
           const uint4 h0 = *reinterpret_cast<const uint4 *>(sA + o0), l0 = *reinterpret_cast<const uint4 *>(sA + pl.a_plane + o0);
-          const uint4 h1 = *reinterpret_cast<const uint4 *>(sA + o1), l1 = *reinterpret_cast<const uint4 *>(sA + pl.a_plane + o1);
-          unpack8(h0, l0, hp); unpack8(h1, l1, hp + 8);
+          unpack8(h0, l0, hp);
           tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { ar[i] = 0.f; au[i] = 0.f; an[i] = 0.f; hp[i] = 0.f; }
+          for (int i = 0; i < 8; ++i) { ar[i] = 0.f; au[i] = 0.f; an[i] = 0.f; hp[i] = 0.f; }
         }
-        // gate by gate, so that only one pair of bias vectors is live at a time (register budget: 204 per thread)
-        float hn[16];
+        float hn[8], ng[8];
         {
-          float bi[16], bh[16];
-          ldg16(a.b_ih + ug, bi); ldg16(a.b_hh + ug, bh);
+          float bni[8], bnh[8];                // ... the n biases while r and u are computed
+          ldg8(a.b_ih + 2 * E + ug, bni); ldg8(a.b_hh + 2 * E + ug, bnh);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) ar[i] = fast_sigmoid(mk * xr[i] + bi[i] + (ar[i] + bh[i]));            // r
-          ldg16(a.b_ih + E + ug, bi); ldg16(a.b_hh + E + ug, bh);
+          for (int i = 0; i < 8; ++i) ar[i] = fast_sigmoid(mk * xr[i] + bri[i] + (ar[i] + brh[i]));          // r
 #pragma unroll
-          for (int i = 0; i < 16; ++i) au[i] = fast_sigmoid(mk * xu[i] + bi[i] + (au[i] + bh[i]));            // u (z in torch's naming)
-          ldg16(a.b_ih + 2 * E + ug, bi); ldg16(a.b_hh + 2 * E + ug, bh);
+          for (int i = 0; i < 8; ++i) au[i] = fast_sigmoid(mk * xu[i] + bui[i] + (au[i] + buh[i]));          // u (z in torch's naming)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            an[i] += bh[i];                                                                                  // h-side n pre-activation
-            xn[i] = fast_tanh(mk * xn[i] + bi[i] + ar[i] * an[i]);                                           // n
-            hn[i] = xn[i] + au[i] * (hp[i] - xn[i]);                                                         // h' = (1 - u) n + u h
+          for (int i = 0; i < 8; ++i) {
+            an[i] += bnh[i];                                                                                // h-side n pre-activation
+            ng[i] = fast_tanh(mk * xn[i] + bni[i] + ar[i] * an[i]);                                         // n
+            hn[i] = ng[i] + au[i] * (hp[i] - ng[i]);                                                        // h' = (1 - u) n + u h
           }
         }
-        uint4 hi0, lo0, hi1, lo1;
-        {
-          const float v0[8] = {hn[0], hn[1], hn[2], hn[3], hn[4], hn[5], hn[6], hn[7]};
-          const float v1[8] = {hn[8], hn[9], hn[10], hn[11], hn[12], hn[13], hn[14], hn[15]};
-          split8(v0, hi0, lo0);
-          split8(v1, hi1, lo1);
+        if (j + 1 < nch) {  // the next chunk's input projections travel while this chunk's state / stash is packed and stored
+          const int ugn = ug + 8;
+          ldt8(a.xp, xr_row, ugn, 3 * E, xr); ldt8(a.xp, xr_row, E + ugn, 3 * E, xu); ldt8(a.xp, xr_row, 2 * E + ugn, 3 * E, xn);
         }
+        uint4 hi0, lo0;
+        split8(hn, hi0, lo0);
         if (!lastStep) {  // new state into the operand planes of both CTAs (nobody reads h_{s-1} any more: mma_done)
           *reinterpret_cast<uint4 *>(sA + o0) = hi0; *reinterpret_cast<uint4 *>(sA + pl.a_plane + o0) = lo0;
-          *reinterpret_cast<uint4 *>(sA + o1) = hi1; *reinterpret_cast<uint4 *>(sA + pl.a_plane + o1) = lo1;
           *reinterpret_cast<uint4 *>(peerA + o0) = hi0; *reinterpret_cast<uint4 *>(peerA + pl.a_plane + o0) = lo0;
-          *reinterpret_cast<uint4 *>(peerA + o1) = hi1; *reinterpret_cast<uint4 *>(peerA + pl.a_plane + o1) = lo1;
         }
         if (row_ok) {
           if (a.stash) {
-            if (a.hs) stt16(a.hs + (size_t)s * Mp * E, m, ug, E, hn);
+            if (a.hs) stt8(a.hs + (size_t)s * Mp * E, m, ug, E, hn);
             if (a.hp_hi) {
               const size_t o1e = ((size_t)s * a.M + m) * E + ug;
-              __nv_bfloat16 *ph_ = (__nv_bfloat16 *)a.hp_hi + o1e;
-              *reinterpret_cast<uint4 *>(ph_) = hi0; *reinterpret_cast<uint4 *>(ph_ + 8) = hi1;
-              if (a.hp_lo) {
-                __nv_bfloat16 *pl_ = (__nv_bfloat16 *)a.hp_lo + o1e;
-                *reinterpret_cast<uint4 *>(pl_) = lo0; *reinterpret_cast<uint4 *>(pl_ + 8) = lo1;
-              }
+              st_stream_u4((__nv_bfloat16 *)a.hp_hi + o1e, hi0);
+              if (a.hp_lo) st_stream_u4((__nv_bfloat16 *)a.hp_lo + o1e, lo0);
             }
             if (a.gates) {
               float *gstep = reinterpret_cast<float *>(a.gates) + (size_t)s * Mp * 3 * E;  // per-step blocks of Mp * 3E floats in both formats
               if (a.gates16) {
-                uint32_t w[8];
+                uint32_t w[4];
 #pragma unroll
                 for (int g = 0; g < 3; ++g) {
-                  const float *src = g == 0 ? ar : (g == 1 ? au : xn);
+                  const float *src = g == 0 ? ar : (g == 1 ? au : ng);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i)
-                    w[i] = g < 2 ? pack_u16(q_unorm16(src[2 * i]), q_unorm16(src[2 * i + 1])) : pack_u16(q_snorm16(src[2 * i]), q_snorm16(src[2 * i + 1]));
-                  unsigned short *gq = u16_ptr(gstep, m, g * E + ug, 3 * E);
-                  *reinterpret_cast<uint4 *>(gq) = make_uint4(w[0], w[1], w[2], w[3]);
-                  *reinterpret_cast<uint4 *>(gq + 256) = make_uint4(w[4], w[5], w[6], w[7]);
+                  for (int i = 0; i < 4; ++i)  // sigmoid / tanh outputs already lie in [0, 1] / [-1, 1]: no clamp needed
+                    w[i] = g < 2 ? pack_u16((unsigned short)__float2uint_rn(src[2 * i] * 65535.0f), (unsigned short)__float2uint_rn(src[2 * i + 1] * 65535.0f))
+                                 : pack_u16((unsigned short)(short)__float2int_rn(src[2 * i] * 32767.0f), (unsigned short)(short)__float2int_rn(src[2 * i + 1] * 32767.0f));
+                  st_stream_u4(u16_ptr(gstep, m, g * E + ug, 3 * E), make_uint4(w[0], w[1], w[2], w[3]));
                 }
               } else {
-                stt16(gstep, m, ug, 3 * E, ar); stt16(gstep, m, E + ug, 3 * E, au); stt16(gstep, m, 2 * E + ug, 3 * E, xn);
+                stt8(gstep, m, ug, 3 * E, ar); stt8(gstep, m, E + ug, 3 * E, au); stt8(gstep, m, 2 * E + ug, 3 * E, ng);
               }
             }
-            if (a.ahn) stt16(a.ahn + (size_t)s * Mp * E, m, ug, E, an);
+            if (a.ahn) stt8(a.ahn + (size_t)s * Mp * E, m, ug, E, an);
           }
           if (lastStep && a.cond) {
             float *cd = a.cond + m * a.cond_ld + ug;
-            if (cond_vec) st16(cd, hn);
-            else {
+            if (cond_vec) {
+              *reinterpret_cast<float4 *>(cd) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+              *reinterpret_cast<float4 *>(cd + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+            } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) cd[i] = hn[i];
+              for (int i = 0; i < 8; ++i) cd[i] = hn[i];
             }
           }
         }
       }
       if (!lastStep) {
         fence_before();      // this warp's accumulator reads are complete before the next products overwrite them
-        fence_async_smem();  // the new state is visible to the tensor cores of both CTAs
+        fence_async_smem();  // the new state is visible to the tensor cores
         __syncwarp();
         if (lane == 0) { mbar_arrive_cluster(ready_own); mbar_arrive_cluster(ready_peer); }
       }
@@ -380,7 +388,7 @@ enc_gru_fwd_persist(const FwdArgs a, const __grid_constant__ CUtensorMap map_hi,
   fence_before();
   __syncthreads();
   cluster.sync();  // no CTA leaves while its peer may still write into its planes or signal its barriers
-  if (warp == kEpiWarps + 1) {
+  if (warp == kFwdGateWarps + 1) {
     fence_after();
     tmem_dealloc(tmem, kTmemCols);
   }
@@ -406,9 +414,9 @@ int launch_fwd(const FwdArgs &a, cudaStream_t st) {
   LFI_TRY(tc::make_plane_map(&mhi, a.whh_hi, 3 * a.E, a.E, a.E, 0, 1, 64));
   if (a.nplanes == 2) LFI_TRY(tc::make_plane_map(&mlo, a.whh_lo, 3 * a.E, a.E, a.E, 0, 1, 64));
   else mlo = mhi;
-  static const bool timing = env_flag("LFI_ENC_TIMING", false);
+  static const int timing = env_flag("LFI_ENC_TIMING", false) ? 1 : 0;
   FwdArgs at = a;
-  at.timing = timing ? 1 : 0;
+  at.timing = timing;
   static bool attr_set = false;
   if (!attr_set) {
     LFI_CUDA(cudaFuncSetAttribute(enc_gru_fwd_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -418,7 +426,7 @@ int launch_fwd(const FwdArgs &a, cudaStream_t st) {
   // > half of the SM's shared memory: never two CTAs (each wanting all 512 TMEM columns) on one SM
   const int smem = p.total < 120 * 1024 ? 120 * 1024 : p.total;
   dim3 grid(2, ntiles, 1);
-  enc_gru_fwd_persist<<<grid, kThreads, smem, st>>>(at, mhi, mlo);
+  enc_gru_fwd_persist<<<grid, kFwdThreads, smem, st>>>(at, mhi, mlo);
   LFI_LAUNCH_CHECK();
   return LFI_OK;
 }
@@ -470,9 +478,11 @@ __device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t saddr, uint32_t lbo_b
 }
 
 // Sum over the 32 lanes of 64 values per lane; lane l ends up with the totals of indices 2l and 2l+1 (in v[0], v[1]).
-__device__ __forceinline__ void warp_reduce64(float (&v)[64], int lane) {
+
+// Sum over the 32 lanes of 32 values per lane; lane l ends up with the total of index l (in v[0]).
+__device__ __forceinline__ void warp_reduce32(float (&v)[32], int lane) {
 #pragma unroll
-  for (int half = 32, bit = 16; half >= 2; half >>= 1, bit >>= 1) {
+  for (int half = 16, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
     const bool upper = (lane & bit) != 0;
 #pragma unroll
     for (int i = 0; i < half; ++i) {
@@ -485,6 +495,7 @@ __device__ __forceinline__ void warp_reduce64(float (&v)[64], int lane) {
 
 }  // namespace
 
+template <bool G16>  // gate stash in 16-bit fixed point (the tensor-core modes' default) or fp32
 __global__ void __launch_bounds__(kThreads, 1)
 enc_gru_bwd_persist(const BwdArgs a, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
   extern __shared__ __align__(16) uint8_t smraw[];
@@ -516,8 +527,30 @@ enc_gru_bwd_persist(const BwdArgs a, const __grid_constant__ CUtensorMap map_hi,
   if (warp == kEpiWarps) {
     // ============================== TMA producer: W_hh rows of (chunk, plane, gate) as MN-major blocks ===================
     if (lane == 0) {
+      // The stash of a step is read once, 2 GB after it was written: it comes from HBM.  One thread asks the L2 for the NEXT
+      // step's blocks of this tile (the row-interleaved layout makes them whole contiguous ranges per 32-window group) while
+      // the gate warps work on the current one, so that their loads pay L2 latency instead of HBM latency.
+      const size_t Mp = tiled_rows((size_t)a.M);
+      const size_t g0 = (size_t)blockIdx.x * (kRows / 32), g1 = min(g0 + kRows / 32, Mp / 32);
+      auto prefetch_step = [&](int s) {
+        if (s < 0) return;
+        const size_t gbytes = (size_t)3 * E * (a.gates16 ? 64 : 128), ebytes = (size_t)E * 128;  // bytes per 32-window group
+        const char *gb = reinterpret_cast<const char *>(a.gates) + (size_t)s * Mp * 3 * E * sizeof(float);
+        const char *ab = reinterpret_cast<const char *>(a.ahn + (size_t)s * Mp * E);
+        for (size_t gq = g0; gq < g1; ++gq) {
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gb + gq * gbytes), "r"((uint32_t)gbytes) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ab + gq * ebytes), "r"((uint32_t)ebytes) : "memory");
+          if (s > 0) {
+            const char *hb = reinterpret_cast<const char *>(a.hs + (size_t)(s - 1) * Mp * E);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(hb + gq * ebytes), "r"((uint32_t)ebytes) : "memory");
+          }
+        }
+      };
+      prefetch_step(hist - 1);
+      prefetch_step(hist - 2);
       int st = 0; uint32_t ph = 0;
-      for (int it = 0; it < nit; ++it)
+      for (int it = 0; it < nit; ++it) {
+        prefetch_step(hist - 3 - it);
         for (int j = 0; j < nch; ++j)
           for (int p = 0; p < a.nplanes; ++p)
             for (int g = 0; g < 3; ++g) {
@@ -528,6 +561,7 @@ enc_gru_bwd_persist(const BwdArgs a, const __grid_constant__ CUtensorMap map_hi,
               for (int i = 0; i < E / 64; ++i) tma_load_3d(dst + i * 4096, mp, &full[st], 64 * i, g * E + kCU * j, 0);
               if (++st == pl.stages) { st = 0; ph ^= 1; }
             }
+      }
     }
   } else if (warp == kEpiWarps + 1) {
     // ============================== MMA issuer ==============================================================================
@@ -582,6 +616,42 @@ enc_gru_bwd_persist(const BwdArgs a, const __grid_constant__ CUtensorMap map_hi,
     const bool tm = a.timing && blockIdx.x == 0 && tid == 0;
     long long t_wait = 0, t_gate = 0;
     int cc = 0;
+    // raw stash of one sub-chunk (8 units of this window): requested one sub-chunk ahead, so that its latency (L2: the TMA warp
+    // prefetches each step's stash from HBM) overlaps the packing / stores / reduction of the previous sub-chunk
+    struct Raw { uint4 g[3]; float gf[3][8]; float an[8], hp[8], dd[8]; };
+    auto load_raw = [&](int s, int it, int ug, uint4 (&g16)[3], float (&gf)[3][G16 ? 1 : 8], float (&an)[8], float (&hp)[8], float (&dd)[8]) {
+      const float *gstep = reinterpret_cast<const float *>(a.gates) + (size_t)s * Mp * 3 * E;
+      if constexpr (G16) {
+        const unsigned short *base = reinterpret_cast<const unsigned short *>(gstep);
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+          asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(g16[g].x), "=r"(g16[g].y), "=r"(g16[g].z), "=r"(g16[g].w)
+                       : "l"(base + ((m >> 5) * (size_t)((3 * E) >> 3) + (size_t)((g * E + ug) >> 3)) * 256 + (m & 31) * 8));
+      } else {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          float t[8];
+          ldt8(gstep, m, g * E + ug, 3 * E, t);
+#pragma unroll
+          for (int i = 0; i < (G16 ? 1 : 8); ++i) gf[g][i] = t[i];
+        }
+      }
+      ldt8(a.ahn + (size_t)s * Mp * E, m, ug, E, an);
+      if (s > 0) ldt8(a.hs + (size_t)(s - 1) * Mp * E, m, ug, E, hp);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hp[i] = 0.f;
+      }
+      if (it > 0) ldt8(a.dhd, m, ug, E, dd);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dd[i] = 0.f;
+      }
+    };
+    uint4 ng16[3]; float ngf[3][G16 ? 1 : 8], nan_[8], nhp[8], ndd[8];  // "next" register set
+    load_raw(hist - 1, 0, 16 * sub, ng16, ngf, nan_, nhp, ndd);
+    const int nsub = 2 * nch;  // sub-chunks per step
     for (int it = 0; it < hist; ++it) {
       const int s = hist - 1 - it;
       const long long c0 = tm ? clock64() : 0;
@@ -592,58 +662,55 @@ enc_gru_bwd_persist(const BwdArgs a, const __grid_constant__ CUtensorMap map_hi,
       const long long c1 = tm ? clock64() : 0;
       t_wait += c1 - c0;
       const uint32_t tcur = tlane + (uint32_t)((it & 1) * 256);
-      const float *gstep = reinterpret_cast<const float *>(a.gates) + (size_t)s * Mp * 3 * E;
-      for (int j = 0; j < nch; ++j) {
-        const int ug = kCU * j + 16 * sub;
-        float rg[16], ugt[16], ng[16], an[16], hp[16], dh[16];
-        // ---- loads (tiled: coalesced) ----
-        if (a.gates16) {
-          const unsigned short *base = reinterpret_cast<const unsigned short *>(gstep);
+      for (int i2 = 0; i2 < nsub; ++i2) {
+        const int j = i2 >> 1, half = i2 & 1;
+        const int ug = kCU * j + 16 * sub + 8 * half;
+        float rg[8], ugt[8], ng[8], an[8], hp[8], dh[8];
+        // ---- this sub-chunk's operands (requested one sub-chunk ago) ----
+        if constexpr (G16) {
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
-            const unsigned short *gq = base + ((m >> 5) * (size_t)((3 * E) >> 3) + (size_t)((g * E + ug) >> 3)) * 256 + (m & 31) * 8;
-            const uint4 w0 = __ldg(reinterpret_cast<const uint4 *>(gq)), w1 = __ldg(reinterpret_cast<const uint4 *>(gq + 256));
-            const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const uint32_t w[4] = {ng16[g].x, ng16[g].y, ng16[g].z, ng16[g].w};
             float *dst = g == 0 ? rg : (g == 1 ? ugt : ng);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
               if (g < 2) { dst[2 * i] = dq_unorm16((unsigned short)(w[i] & 0xffff)); dst[2 * i + 1] = dq_unorm16((unsigned short)(w[i] >> 16)); }
               else { dst[2 * i] = dq_snorm16((unsigned short)(w[i] & 0xffff)); dst[2 * i + 1] = dq_snorm16((unsigned short)(w[i] >> 16)); }
             }
           }
         } else {
-          ldt16(gstep, m, ug, 3 * E, rg); ldt16(gstep, m, E + ug, 3 * E, ugt); ldt16(gstep, m, 2 * E + ug, 3 * E, ng);
-        }
-        ldt16(a.ahn + (size_t)s * Mp * E, m, ug, E, an);
-        if (s > 0) ldt16(a.hs + (size_t)(s - 1) * Mp * E, m, ug, E, hp);
-        else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) hp[i] = 0.f;
+          for (int i = 0; i < (G16 ? 1 : 8); ++i) { rg[i] = ngf[0][i]; ugt[i] = ngf[1][i]; ng[i] = ngf[2][i]; }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { an[i] = nan_[i]; hp[i] = nhp[i]; }
         if (it > 0) {
-          tmem_ld16(tcur + ug, dh);                 // (dA_h(s+1) W_hh)[:, ug..]
-          float dd[16];
-          ldt16(a.dhd, m, ug, E, dd);              // + dh_{s+1} * u_{s+1}
+          tmem_ld8(tcur + ug, dh);                  // (dA_h(s+1) W_hh)[:, ug..]
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dh[i] += dd[i];
+          for (int i = 0; i < 8; ++i) dh[i] += ndd[i];   // + dh_{s+1} * u_{s+1}
         } else {
           if (a.dh_extra) {
             const float *ex = a.dh_extra + m * a.dh_extra_ld + ug;
-            if (extra_vec) ld16(ex, dh);
-            else {
+            if (extra_vec) {
+              const float4 t0 = *reinterpret_cast<const float4 *>(ex), t1 = *reinterpret_cast<const float4 *>(ex + 4);
+              dh[0] = t0.x; dh[1] = t0.y; dh[2] = t0.z; dh[3] = t0.w; dh[4] = t1.x; dh[5] = t1.y; dh[6] = t1.z; dh[7] = t1.w;
+            } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) dh[i] = ex[i];
+              for (int i = 0; i < 8; ++i) dh[i] = ex[i];
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) dh[i] = 0.f;
+            for (int i = 0; i < 8; ++i) dh[i] = 0.f;
           }
         }
+        // ---- request the next sub-chunk (of this step, or the first one of the next step) ----
+        if (i2 + 1 < nsub) load_raw(s, it, kCU * ((i2 + 1) >> 1) + 16 * sub + 8 * ((i2 + 1) & 1), ng16, ngf, nan_, nhp, ndd);
+        else if (s > 0) load_raw(s - 1, it + 1, 16 * sub, ng16, ngf, nan_, nhp, ndd);
         // ---- gate backward (aux::enc_gate_bwd2 semantics) ----
-        float dar[16], dau[16], dan[16], danr[16];
+        float dar[8], dau[8], dan[8], danr[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
           const float dn = dh[i] * (1.0f - ugt[i]), du = dh[i] * (hp[i] - ng[i]);
           dan[i] = dn * (1.0f - ng[i] * ng[i]);
           dau[i] = du * ugt[i] * (1.0f - ugt[i]);
@@ -651,92 +718,86 @@ enc_gru_bwd_persist(const BwdArgs a, const __grid_constant__ CUtensorMap map_hi,
           danr[i] = dan[i] * rg[i];
           dh[i] *= ugt[i];                          // direct part for step s-1
         }
-        if (s > 0 && row_ok) stt16(a.dhd, m, ug, E, dh);
+        if (s > 0 && row_ok) stt8(a.dhd, m, ug, E, dh);
         // ---- operand planes of the chunk for dh_{s-1} += dA_h W_hh (K index = unit inside the chunk) ----
+        const int buf = cc & 1;
         if (s > 0) {
-          const int buf = cc & 1;
-          mbar_wait(&a_empty[buf], (uint32_t)(((cc >> 1) & 1) ^ 1));
+          if (half == 0) mbar_wait(&a_empty[buf], (uint32_t)(((cc >> 1) & 1) ^ 1));
           uint8_t *ab = sA + buf * kABuf;
-          const uint32_t o0 = sw64_off(L, 2 * sub), o1 = sw64_off(L, 2 * sub + 1);
+          const uint32_t o0 = sw64_off(L, 2 * sub + half);
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
             const float *src = g == 0 ? dar : (g == 1 ? dau : danr);
             const float v0[8] = {src[0], src[1], src[2], src[3], src[4], src[5], src[6], src[7]};
-            const float v1[8] = {src[8], src[9], src[10], src[11], src[12], src[13], src[14], src[15]};
-            uint4 h0, l0, h1, l1;
-            split8(v0, h0, l0); split8(v1, h1, l1);
-            *reinterpret_cast<uint4 *>(ab + g * kAGate + o0) = h0; *reinterpret_cast<uint4 *>(ab + g * kAGate + o1) = h1;
-            *reinterpret_cast<uint4 *>(ab + 3 * kAGate + g * kAGate + o0) = l0; *reinterpret_cast<uint4 *>(ab + 3 * kAGate + g * kAGate + o1) = l1;
+            uint4 h0, l0;
+            split8(v0, h0, l0);
+            *reinterpret_cast<uint4 *>(ab + g * kAGate + o0) = h0;
+            *reinterpret_cast<uint4 *>(ab + 3 * kAGate + g * kAGate + o0) = l0;
           }
-          fence_before();
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_full[buf])) : "memory");
+          if (half == 1) {
+            fence_before();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_full[buf])) : "memory");
           }
         }
-        ++cc;
-        // ---- gate gradients for the weight-gradient GEMMs: gate-interleaved columns, transposed through shared memory ----
+        if (half == 1) ++cc;
+        // ---- gate gradients for the weight-gradient GEMMs: gate-interleaved columns (24 values = 3 pieces of 16 bytes per
+        //      window and plane), transposed through shared memory so that a store instruction covers whole 48-byte runs ----
         {
-          uint4 hi6[6], lo6[6];
-#pragma unroll
-          for (int k = 0; k < 6; ++k) {
-            float v[8];
-#pragma unroll
-            for (int x = 0; x < 8; ++x) {
-              const int e = 8 * k + x, u = e / 3, g = e - 3 * u;
-              v[x] = g == 0 ? dar[u] : (g == 1 ? dau[u] : danr[u]);
-            }
-            split8(v, hi6[k], lo6[k]);
-          }
           __nv_bfloat16 *planes[2] = {(__nv_bfloat16 *)a.dah3_hi, (__nv_bfloat16 *)a.dah3_lo};
 #pragma unroll
           for (int pp = 0; pp < 2; ++pp) {
             if (planes[pp] == nullptr) continue;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) *reinterpret_cast<uint4 *>(stg + lane * kStgRow + 16 * k) = pp ? lo6[k] : hi6[k];
+            for (int k = 0; k < 3; ++k) {
+              float v[8];
+#pragma unroll
+              for (int x = 0; x < 8; ++x) {
+                const int e = 8 * k + x, u = e / 3, g = e - 3 * u;
+                v[x] = g == 0 ? dar[u] : (g == 1 ? dau[u] : danr[u]);
+              }
+              uint4 hi, lo;
+              split8(v, hi, lo);
+              *reinterpret_cast<uint4 *>(stg + lane * kStgRow + 16 * k) = pp ? lo : hi;
+            }
             __syncwarp();
 #pragma unroll
-            for (int k2 = 0; k2 < 6; ++k2) {
-              const int pc = k2 * 32 + lane, r = pc / 6, piece = pc - 6 * r;
+            for (int k2 = 0; k2 < 3; ++k2) {
+              const int pc = k2 * 32 + lane, r = pc / 3, piece = pc - 3 * r;
               const uint4 val = *reinterpret_cast<const uint4 *>(stg + r * kStgRow + 16 * piece);
               const size_t mr = row0 + r;
               if (mr < (size_t)a.M)
-                *reinterpret_cast<uint4 *>(planes[pp] + ((size_t)s * a.M + mr) * 3 * E + 3 * ug + 8 * piece) = val;
+                st_stream_u4(planes[pp] + ((size_t)s * a.M + mr) * 3 * E + 3 * ug + 8 * piece, val);
             }
             __syncwarp();
           }
-          // da_n: 16 units = 2 pieces per plane; staged as [hi0 hi1 lo0 lo1] per window
+          // da_n: 8 units = 1 piece per plane; staged as [hi lo] per window
           {
-            const float v0[8] = {dan[0], dan[1], dan[2], dan[3], dan[4], dan[5], dan[6], dan[7]};
-            const float v1[8] = {dan[8], dan[9], dan[10], dan[11], dan[12], dan[13], dan[14], dan[15]};
-            uint4 h0, l0, h1, l1;
-            split8(v0, h0, l0); split8(v1, h1, l1);
-            *reinterpret_cast<uint4 *>(stg + lane * kStgRow) = h0; *reinterpret_cast<uint4 *>(stg + lane * kStgRow + 16) = h1;
-            *reinterpret_cast<uint4 *>(stg + lane * kStgRow + 32) = l0; *reinterpret_cast<uint4 *>(stg + lane * kStgRow + 48) = l1;
+            uint4 h0, l0;
+            split8(dan, h0, l0);
+            *reinterpret_cast<uint4 *>(stg + lane * kStgRow) = h0; *reinterpret_cast<uint4 *>(stg + lane * kStgRow + 16) = l0;
             __syncwarp();
 #pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              const int pc = k2 * 32 + lane, r = pc >> 2, piece = pc & 3;
+            for (int k2 = 0; k2 < 2; ++k2) {
+              const int pc = k2 * 32 + lane, r = pc >> 1, piece = pc & 1;
               const uint4 val = *reinterpret_cast<const uint4 *>(stg + r * kStgRow + 16 * piece);
               const size_t mr = row0 + r;
-              __nv_bfloat16 *dst = (__nv_bfloat16 *)(piece < 2 ? a.dan_hi : a.dan_lo);
-              if (mr < (size_t)a.M && dst) *reinterpret_cast<uint4 *>(dst + ((size_t)s * a.M + mr) * E + ug + 8 * (piece & 1)) = val;
+              __nv_bfloat16 *dst = (__nv_bfloat16 *)(piece == 0 ? a.dan_hi : a.dan_lo);
+              if (mr < (size_t)a.M && dst) st_stream_u4(dst + ((size_t)s * a.M + mr) * E + ug, val);
             }
             __syncwarp();
           }
         }
         // ---- bias gradients: column sums over the warp's windows, then shared-memory accumulators ----
         {
-          float v[64];
+          float v[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = row_ok ? dar[i] : 0.f; v[16 + i] = row_ok ? dau[i] : 0.f; v[32 + i] = row_ok ? dan[i] : 0.f; v[48 + i] = row_ok ? danr[i] : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            v[i] = row_ok ? dar[i] : 0.f; v[8 + i] = row_ok ? dau[i] : 0.f; v[16 + i] = row_ok ? dan[i] : 0.f; v[24 + i] = row_ok ? danr[i] : 0.f;
           }
-          warp_reduce64(v, lane);
-          const int idx = 2 * lane, type = idx >> 4, u = idx & 15;
-          atomicAdd(&bacc[type * E + ug + u], v[0]);
-          atomicAdd(&bacc[type * E + ug + u + 1], v[1]);
+          warp_reduce32(v, lane);
+          atomicAdd(&bacc[(lane >> 3) * E + ug + (lane & 7)], v[0]);
         }
       }
       if (tm) t_gate += clock64() - c1;
@@ -781,12 +842,14 @@ int launch_bwd(const BwdArgs &a, cudaStream_t st) {
   at.timing = timing ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
-    LFI_CUDA(cudaFuncSetAttribute(enc_gru_bwd_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LFI_CUDA(cudaFuncSetAttribute(enc_gru_bwd_persist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LFI_CUDA(cudaFuncSetAttribute(enc_gru_bwd_persist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int ntiles = (a.M + kRows - 1) / kRows;
   const int smem = p.total < 120 * 1024 ? 120 * 1024 : p.total;
-  enc_gru_bwd_persist<<<ntiles, kThreads, smem, st>>>(at, mhi, mlo);
+  if (a.gates16) enc_gru_bwd_persist<true><<<ntiles, kThreads, smem, st>>>(at, mhi, mlo);
+  else enc_gru_bwd_persist<false><<<ntiles, kThreads, smem, st>>>(at, mhi, mlo);
   LFI_LAUNCH_CHECK();
   return LFI_OK;
 }

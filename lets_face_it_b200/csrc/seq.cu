@@ -1072,6 +1072,13 @@ int lfi_expand_faces(const float *x, const float *means, const float *stds, size
   return aux::expand_faces(x, means, stds, rows, exp_dim, jaw_dim, neck_dim, out, (cudaStream_t)stream);
 }
 
+int lfi_jerk(const float *x, int B, int T, int C, void *scratch8, float *out, void *stream) {
+  LFI_REQUIRE(x && scratch8 && out && B >= 1 && C >= 1, LFI_ERR_ARG, "lfi_jerk: bad argument");
+  LFI_REQUIRE(T >= 4, LFI_ERR_SHAPE, "lfi_jerk: a third difference needs T >= 4 frames (got %d)", T);
+  LFI_REQUIRE(((uintptr_t)scratch8 & 7) == 0, LFI_ERR_ARG, "lfi_jerk: scratch must be 8-byte aligned");
+  return aux::jerk(x, B, T, C, (double *)scratch8, out, (cudaStream_t)stream);
+}
+
 int lfi_clip_adam(float *theta, float *grad, float *m, float *v, size_t n, float lr, float beta1, float beta2, float eps,
                   float max_norm, float grad_scale, int step, float *norm_scratch, void *stream) {
   LFI_REQUIRE(theta && grad && m && v && norm_scratch && step >= 1, LFI_ERR_ARG, "lfi_clip_adam: bad argument");

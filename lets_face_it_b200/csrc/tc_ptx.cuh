@@ -42,7 +42,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // generic-proxy writes (st.shared, also into the peer CTA) -> visible to the async proxy (tcgen05.mma operand reads)
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// (shared-memory scope: the unqualified fence.proxy.async also orders global memory and compiles to MEMBAR.ALL.GPU, i.e. it
+// waits for every outstanding global store of the thread - stash / plane stores - before each operand hand-off; the operands
+// live in shared memory only.  Writers fence before their release-arrive, the MMA-issuing thread fences again after its acquire.)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {  // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");

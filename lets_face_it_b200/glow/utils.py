@@ -7,12 +7,24 @@ def get_longest_history(cond_params):
 
 
 def calc_jerk(x):
-    """Mean absolute third difference along time of [B, T, C] (utils.py:53-58)."""
-    x = x.cpu()
-    d1 = x[:, 1:] - x[:, :-1]
-    d2 = d1[:, 1:] - d1[:, :-1]
-    d3 = d2[:, 1:] - d2[:, :-1]
-    return d3.abs().mean()
+    """Mean absolute third difference along time of [B, T, C] (utils.py:53-58), the validation metric of
+    mimicry_logger.py:175-184.  The reference moves the frames to the host first (`x.cpu()`); here the generated frames stay
+    where `SeqGlow.inference` left them: one launch (`lfi_jerk`) and a one-float result on the device.  CUDA tensors only."""
+    import torch
+
+    from .. import _cabi as cabi
+
+    if x.device.type != "cuda":
+        raise RuntimeError("lets_face_it_b200.calc_jerk: frames live on %s; the path runs on CUDA only (no CPU path)" % x.device)
+    if x.dim() != 3 or x.shape[1] < 4:
+        raise RuntimeError("calc_jerk expects [B, T >= 4, C] frames, got %s" % (tuple(x.shape),))
+    x = x.detach().to(torch.float32).contiguous()
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(1, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        cabi.check(cabi.lib().lfi_jerk(x.data_ptr(), x.shape[0], x.shape[1], x.shape[2], scratch.data_ptr(), out.data_ptr(),
+                                       cabi.stream_ptr()), "lfi_jerk")
+    return out[0]
 
 
 def test_params(hparams):

@@ -405,6 +405,14 @@ def destandardize_expand(seq, means, stds, exp_dim, jaw_dim, neck_dim):
     return expand_face_dim(seq * stds + means, exp_dim, jaw_dim, neck_dim)
 
 
+def calc_jerk(x):
+    """glow/utils.py:53-58: mean absolute third difference along time of [B, T, C]."""
+    d = x[:, 1:] - x[:, :-1]
+    a = d[:, 1:] - d[:, :-1]
+    j = a[:, 1:] - a[:, :-1]
+    return j.abs().mean()
+
+
 def derange_batch(batch, modalities, permutation):
     """glow/utils.py:85-100 with the permutation drawn by the caller (shuffle_time=False, the only use in the reference)."""
     out = {}

@@ -33,7 +33,7 @@ def reference_function(path, name):
 
 def main():
     import_reference()
-    from glow_pytorch.glow.utils import derange_batch, get_mismatched_modalities
+    from glow_pytorch.glow.utils import calc_jerk, derange_batch, get_mismatched_modalities
 
     hp = load_reference_hparams()
     expand = reference_function(os.path.join(REF_CODE, "glow_pytorch", "generate_motion_from_model.py"), "expand_face_dim")
@@ -53,6 +53,10 @@ def main():
     for k, v in batch.items():
         out["batch_" + k] = v.numpy()
         out["deranged_" + k] = mixed[k].numpy()
+    # validation metric of mimicry_logger.py:175-184: calc_jerk (glow/utils.py:53-58) on seeded frames
+    jx = torch.randn(5, 40, 56, generator=g) * 0.7
+    out["jerk_x"] = jx.numpy()
+    out["jerk"] = np.float32(calc_jerk(jx))
     out["mismatched_modalities"] = np.array(mods)
     out["mismatched_name"] = np.array(name)
     np.savez_compressed(os.path.join(GOLDEN, "kat_post.npz"), **out)

@@ -86,3 +86,19 @@ def test_host_feed_matches_device_steps():
     got = [feed.step(h) for h in hosts] + [feed.flush()]
     assert got[0] is None and feed.flush() is None
     assert got[1:] == pytest.approx(want, rel=1e-6)
+
+
+def test_calc_jerk_on_device_matches_reference_vector():
+    """`calc_jerk` (glow/utils.py:53-58; the validation metric of mimicry_logger.py:175-184) as one device launch against the
+    value the reference computed on the same frames (kat_post.npz), and at the sampling size 1024 x 750 against torch."""
+    from lets_face_it_b200.glow.utils import calc_jerk
+
+    g = load_golden("kat_post")
+    x = torch.from_numpy(np.asarray(g["jerk_x"])).to(DEV)
+    got = calc_jerk(x)
+    assert got.is_cuda and abs(float(got) - float(g["jerk"])) <= 2e-7 * float(g["jerk"])
+    big = torch.randn(1024, 750, 56, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    d = big[:, 1:] - big[:, :-1]
+    a = d[:, 1:] - d[:, :-1]
+    ref = (a[:, 1:] - a[:, :-1]).abs().double().mean()
+    assert abs(float(calc_jerk(big)) - float(ref)) <= 1e-6 * float(ref)
