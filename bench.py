@@ -319,6 +319,40 @@ def run_ours(a):
     e2e = frames_step * a.steps / (ms_e2e / 1e3)
     h2d = sum(v.numel() * 4 for v in host.values())
 
+    # ---- end to end over an HBM-resident corpus: per step the host sends the window table entries
+    #      of the batch (8 bytes per sequence) instead of the 14 MB of overlapping windows; the batch is gathered on the device
+    e2e_res = None
+    try:
+        from lets_face_it_b200.data import ResidentWindows
+        from lets_face_it_b200.train import ResidentFeed
+        import random as _random
+
+        gseg = torch.Generator().manual_seed(100 + rank)
+        nseg, Lseg = 48, 600   # 28,800 frames per rank (19 MB): 25,008 stride-1 windows of 80 frames
+        segs = [{"p1_face": torch.randn(Lseg, hy.C, generator=gseg), "p2_face": torch.randn(Lseg, hy.in_dim["p2_face"], generator=gseg),
+                 "p1_speech": torch.randn(Lseg, hy.in_dim["p1_speech"], generator=gseg),
+                 "p2_speech": torch.randn(Lseg, hy.in_dim["p2_speech"], generator=gseg)} for _ in range(nseg)]
+        ds = ResidentWindows(segs, T, dev, shuffle=True, rng=_random.Random(7 + rank))
+        rfeed = ResidentFeed(trainer, ds)
+        cursor = [0]
+
+        def res_step():
+            i0 = cursor[0]
+            cursor[0] = (i0 + B) % (len(ds) - B)
+            return rfeed.step(torch.arange(i0, i0 + B))
+
+        for _ in range(2):
+            res_step()
+        rfeed.flush()
+        ms_res = timed(lambda: res_step(), a.steps)
+        rfeed.flush()
+        e2e_res = {"value": frames_step * a.steps / (ms_res / 1e3), "unit": "frames/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4,
+                   "ms_per_step": ms_res / a.steps, "corpus_frames_per_gpu": nseg * Lseg,
+                   "note": "ResidentWindows: synthetic corpus resident in HBM, the reference's stride-1 window table, batch gathered on the device"}
+        del ds, rfeed, segs
+    except Exception as e:  # secondary number only
+        e2e_res = {"error": str(e)[:200]}
+
     # ---- autoregressive sampling (second half of the metric): BASELINE.json configs[3] per-GPU share -------------------
     sample = None
     if not a.no_sample:
@@ -332,9 +366,17 @@ def run_ours(a):
         model.inference(START_TS + Tg, data=data)  # full-size warm-up: workspace allocation and first touch stay outside the timed run
         n0 = L.lfi_launch_count()
         ms_s = timed(lambda: model.inference(START_TS + Tg, data=data), 1)
+        sust_s = peaks()[0]
+        fps_gpu = Bs * Tg / (ms_s * 1e-3)
         sample = {"value": Bs * Tg * world / (ms_s * 1e-3), "unit": "frames/s", "sequences_per_gpu": Bs, "frames_per_sequence": Tg, "eps": 0.7,
                   "ms": ms_s, "gpu_launches": int(L.lfi_launch_count() - n0),
-                  "note": "SeqGlow.inference, zero seed frames, temperature 0.7, in-kernel sampler; no collective"}
+                  "note": "SeqGlow.inference, zero seed frames, temperature 0.7; per frame: AR window gather, two tcgen05 conditioning "
+                          "GEMMs, one launch walking the 16 inverse steps - captured as one CUDA graph per chunk of frames; no collective",
+                  # the sampler is a strictly serial chain per sequence (16 inverse steps x 750 frames): latency bound, reported as the
+                  # critical path per frame next to the tensor roofline of its contractions (42.38 MFLOP per frame and sequence)
+                  "roofline": {"bound": "latency", "us_per_frame": 1e3 * ms_s / Tg, "us_per_inverse_step": 1e3 * ms_s / Tg / hy.K,
+                               "achieved": fps_gpu * FLOP_PER_FRAME_FWD / 1e12, "peak": sust_s, "unit": "TFLOP/s",
+                               "frac": fps_gpu * FLOP_PER_FRAME_FWD / 1e12 / sust_s, "peak_source": "measured (sustained)"}}
         del data, hs
         model.train()
 
@@ -354,6 +396,8 @@ def run_ours(a):
     }
     if sample is not None:
         out["sample"] = sample
+    if e2e_res is not None:
+        out["e2e_resident"] = e2e_res
 
     if rank == 0:
         # ---- roofline of the dominant contraction: cond_transform for all 16 steps, [B*56, 920] x [920, 8192] ---------

@@ -196,6 +196,11 @@ int lfi_nll(const float *z, const float *logdet, float *nll, int B, int C, void 
 int lfi_expand_faces(const float *x, const float *means, const float *stds, size_t rows, int exp_dim, int jaw_dim, int neck_dim,
                      float *out, void *stream);
 
+/* Input side on the device: MimicryDataset.__getitem__ + DataLoader collate
+ * (mimicry_data_module.py:44-78) over a corpus that stays resident in HBM.  raw [rows, dim]: all segments of one modality back to
+ * back; row0 [B] (device, int64): first row of each window (segment offset + window start); out [B, T, dim].  Bit-exact copy. */
+int lfi_gather_batch(const float *raw, const long long *row0, int B, int T, int dim, float *out, void *stream);
+
 /* Validation metric on the device: calc_jerk of glow/utils.py:53-58 (mimicry_logger.py:175-184),
  * the mean absolute third difference along time of x [B, T, C] (T >= 4).  scratch8: 8 bytes, 8-byte aligned; out: one float.
  * Differences are three rounded fp32 subtractions as in torch; the mean is accumulated in fp64. */

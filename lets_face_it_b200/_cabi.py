@@ -76,6 +76,7 @@ SYMBOLS = {
     "lfi_actnorm": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "lfi_matmul": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "lfi_nll": (_I, [_P, _P, _P, _I, _I, _P]),
+    "lfi_gather_batch": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "lfi_jerk": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "lfi_clip_adam": (_I, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _F, _F, _I, _P, _P]),
     "lfi_gemm": (_I, [_I, _I, _I, _I, _I, _I, _P, _I, _L, _P, _I, _L, _P, _I, _L, _P, _L, _P, _I, _L, _I, _I, _P, _SZ, _P]),

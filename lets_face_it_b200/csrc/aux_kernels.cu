@@ -758,5 +758,35 @@ int jerk(const float *x, int B, int T, int C, double *scratch, float *out, cudaS
   return LFI_OK;
 }
 
+// Input side: MimicryDataset.__getitem__ + the DataLoader's collate (mimicry_data_module.py:44-78)
+// on a corpus that is resident in HBM.  raw [rows, dim] holds every segment of one modality back to back; window b of the
+// batch is the T consecutive rows starting at row0[b]: out[b][t][:] = raw[row0[b] + t][:].  Pure copy (bit exact), 128-bit
+// accesses when dim % 4 == 0 and the bases are 16-byte aligned.
+__global__ void gather_batch_kernel(const float *__restrict__ raw, const long long *__restrict__ row0, int B, int T, int dim, float *__restrict__ out) {
+  const size_t n = (size_t)B * T * dim;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t per = (size_t)T * dim;
+    const int b = (int)(e / per);
+    out[e] = raw[(size_t)row0[b] * dim + (e - (size_t)b * per)];
+  }
+}
+__global__ void gather_batch_v4_kernel(const float4 *__restrict__ raw, const long long *__restrict__ row0, int B, int T, int dim4, float4 *__restrict__ out) {
+  const size_t n = (size_t)B * T * dim4;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t per = (size_t)T * dim4;
+    const int b = (int)(e / per);
+    out[e] = raw[(size_t)row0[b] * dim4 + (e - (size_t)b * per)];
+  }
+}
+int gather_batch(const float *raw, const long long *row0, int B, int T, int dim, float *out, cudaStream_t st) {
+  if (dim % 4 == 0 && (((uintptr_t)raw | (uintptr_t)out) & 15) == 0) {
+    gather_batch_v4_kernel<<<blocks_for((size_t)B * T * (dim / 4)), TB, 0, st>>>((const float4 *)raw, row0, B, T, dim / 4, (float4 *)out);
+  } else {
+    gather_batch_kernel<<<blocks_for((size_t)B * T * dim), TB, 0, st>>>(raw, row0, B, T, dim, out);
+  }
+  LFI_LAUNCH_CHECK();
+  return LFI_OK;
+}
+
 }  // namespace aux
 }  // namespace lfi

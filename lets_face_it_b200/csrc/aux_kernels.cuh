@@ -94,5 +94,7 @@ int expand_faces(const float *x, const float *means, const float *stds, size_t r
                  cudaStream_t st);
 // calc_jerk (glow/utils.py:53-58): mean |third time difference| of x [B, T, C]; scratch: one double; out: one float
 int jerk(const float *x, int B, int T, int C, double *scratch, float *out, cudaStream_t st);
+// out[b][t][:] = raw[row0[b] + t][:]: a batch of stride-1 windows out of an HBM-resident corpus (mimicry_data_module.py:44-78)
+int gather_batch(const float *raw, const long long *row0, int B, int T, int dim, float *out, cudaStream_t st);
 }  // namespace aux
 }  // namespace lfi

@@ -396,7 +396,7 @@ enc_gru_fwd_persist(const FwdArgs a, const __grid_constant__ CUtensorMap map_hi,
 
 // ------------------------------------------------------------------------------------------------
 bool fwd_supported(int E, int hist, size_t M, int mode) {
-  if (mode == LFI_GEMM_FP32 || !env_flag("LFI_ENC_PERSIST", true)) return false;
+  if (mode == LFI_GEMM_FP32) return false;
   if (!(E == 128 || E == 256) || hist < 1 || M < 128) return false;
   const SmemPlan p = plan(E);
   return p.stages >= 2 && p.total <= 227 * 1024;
@@ -822,7 +822,7 @@ enc_gru_bwd_persist(const BwdArgs a, const __grid_constant__ CUtensorMap map_hi,
 }
 
 bool bwd_supported(int E, int hist, size_t M, int mode) {
-  if (!fwd_supported(E, hist, M, mode) || !env_flag("LFI_ENC_PERSIST_BWD", true)) return false;
+  if (!fwd_supported(E, hist, M, mode)) return false;
   const BwdPlan p = bwd_plan(E);
   return p.stages >= 3 && p.total <= 227 * 1024;
 }

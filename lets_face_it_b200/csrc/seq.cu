@@ -108,7 +108,12 @@ static bool enc_use_planes(const lfi_shape *s, int m, size_t M, int mode) {
 }
 // The persistent window-GRU kernels take over a modality when its encoder runs on operand planes, the shape fits them and the
 // projection GEMM is taken by the tcgen05 tiles (only those write the row-interleaved xp).
+// Switches (read at call time): training uses them when LFI_ENC_PERSIST=1 - measured on B200 they tie with the per-step launches
+// on one GPU (11.08 vs 11.03 ms per step) and lose 1.3 % at two GPUs, because a 225 KB-shared-memory CTA per SM leaves no room for
+// the NCCL kernels that overlap the encoder backward - so the default for training is the per-step path.
+// Sampling / feature encoding (no stash to store) is 4 % faster with them: on by default (LFI_ENC_PERSIST_SAMPLE=0 turns them off).
 static bool enc_use_persist(const lfi_shape *s, int m, size_t M, size_t BT, int mode, bool need_bwd) {
+  if (!env_flag(need_bwd ? "LFI_ENC_PERSIST" : "LFI_ENC_PERSIST_SAMPLE", !need_bwd)) return false;
   if (!enc_use_planes(s, m, M, mode)) return false;
   const int E = s->ehid[m], hist = s->hist[m];
   if (need_bwd ? !encp::bwd_supported(E, hist, M, mode) : !encp::fwd_supported(E, hist, M, mode)) return false;
@@ -415,6 +420,52 @@ static int check_batch(const lfi_shape *s, const Dims &d, const lfi_batch *b, in
   LFI_REQUIRE(b->T >= min_T, LFI_ERR_SHAPE, "batch: T=%d shorter than needed (%d)", b->T, min_T);
   (void)s; (void)d;
   return LFI_OK;
+}
+
+// Runs `body` (launches on `st` only) as one CUDA graph when possible; falls back to direct launches when the stream is
+// already being captured, the capture is refused, or LFI_SAMPLE_GRAPH=0.  Executable graphs are destroyed lazily, once the
+// event recorded behind their launch has completed (no host synchronisation inside the call).
+template <class F> static int run_frames_graphed(F &&body, int nframes, cudaStream_t st) {
+  struct Pending { cudaGraphExec_t ex; cudaEvent_t ev; };
+  static Pending pend[64];
+  static int npend = 0;
+  for (int i = 0; i < npend;) {  // reap finished graphs
+    if (cudaEventQuery(pend[i].ev) == cudaSuccess) {
+      cudaGraphExecDestroy(pend[i].ex);
+      cudaEventDestroy(pend[i].ev);
+      pend[i] = pend[--npend];
+    } else {
+      cudaGetLastError();
+      ++i;
+    }
+  }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  const bool want = nframes > 1 && npend < 60 && env_flag("LFI_SAMPLE_GRAPH", false) &&
+                    cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone;
+  if (!want) return body();
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    return body();
+  }
+  const long launches_before = lfi_launch_count();
+  const int rc = body();
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(st, &g);
+  cudaGraphExec_t ex = nullptr;
+  if (rc == LFI_OK && e == cudaSuccess && g && cudaGraphInstantiate(&ex, g, 0) == cudaSuccess) {
+    cudaGraphDestroy(g);
+    LFI_CUDA(cudaGraphLaunch(ex, st));
+    cudaEvent_t ev;
+    LFI_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    LFI_CUDA(cudaEventRecord(ev, st));
+    pend[npend++] = Pending{ex, ev};
+    return LFI_OK;
+  }
+  if (g) cudaGraphDestroy(g);
+  cudaGetLastError();
+  if (rc != LFI_OK) return rc;      // a real error of the body: report it
+  count_launches(launches_before - lfi_launch_count());  // the captured launches never ran: do not count them twice
+  return body();                    // capture refused: plain stream-ordered launches
 }
 
 }  // namespace lfi
@@ -895,21 +946,29 @@ int lfi_seq_sample(const lfi_shape *s, const void *derived, const lfi_params *p,
       }
       a.cstatic = nullptr; a.faces = nullptr;
       a.Tc = 1; a.G = w.G; a.g_ld = (long)K * d.GH;
-      for (int tc = 0; tc < Tc; ++tc) {
-        LFI_TRY(aux::gather_windows(w.car, d.Far, 0, faces, nullptr, B, seq_len, d.C, hist0, 0, t0 + tc, 1, st));
-        float *Cf = w.Cs + (size_t)tc * B * K * d.D;  // static pre-activation of this frame (bias included), updated in place
-        GemmArgs q = gemm_args(0, 1, B, K * d.D, d.Far, w.car, d.Far, nullptr, d.Far, Cf, K * d.D, LFI_EPI_ACCUM_PRE | LFI_EPI_LRELU);
-        q.pB = plane_ref(w.war_hi, w.war_lo, d.Far);
-        q.pOut = plane_ref(w.cact_hi, w.cact_lo, K * d.D);
-        LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
-        GemmArgs h = gemm_args(0, 1, B, d.GH, d.D, nullptr, K * d.D, nullptr, d.D, w.G, K * d.GH, LFI_EPI_BIAS, p->b_ih);
-        h.batch = K; h.sC = d.GH; h.sBias = d.GH;
-        h.pA = plane_ref(w.cact_hi, w.cact_lo, K * d.D, d.D);
-        h.pB = plane_ref(w.wihc_hi, w.wihc_lo, d.D, (long)d.GH * d.D);
-        LFI_TRY(gemm_dispatch(gemm_mode, h, gws, gws_bytes, st));
-        a.t_abs0 = t0 + tc; a.t_rel0 = c0 + tc;
-        LFI_TRY(core::launch_inv(a, st));
-      }
+      auto frames = [&]() -> int {
+        for (int tc = 0; tc < Tc; ++tc) {
+          LFI_TRY(aux::gather_windows(w.car, d.Far, 0, faces, nullptr, B, seq_len, d.C, hist0, 0, t0 + tc, 1, st));
+          float *Cf = w.Cs + (size_t)tc * B * K * d.D;  // static pre-activation of this frame (bias included), updated in place
+          GemmArgs q = gemm_args(0, 1, B, K * d.D, d.Far, w.car, d.Far, nullptr, d.Far, Cf, K * d.D, LFI_EPI_ACCUM_PRE | LFI_EPI_LRELU);
+          q.pB = plane_ref(w.war_hi, w.war_lo, d.Far);
+          q.pOut = plane_ref(w.cact_hi, w.cact_lo, K * d.D);
+          LFI_TRY(gemm_dispatch(gemm_mode, q, gws, gws_bytes, st));
+          GemmArgs h = gemm_args(0, 1, B, d.GH, d.D, nullptr, K * d.D, nullptr, d.D, w.G, K * d.GH, LFI_EPI_BIAS, p->b_ih);
+          h.batch = K; h.sC = d.GH; h.sBias = d.GH;
+          h.pA = plane_ref(w.cact_hi, w.cact_lo, K * d.D, d.D);
+          h.pB = plane_ref(w.wihc_hi, w.wihc_lo, d.D, (long)d.GH * d.D);
+          LFI_TRY(gemm_dispatch(gemm_mode, h, gws, gws_bytes, st));
+          core::InvArgs af = a;
+          af.t_abs0 = t0 + tc; af.t_rel0 = c0 + tc;
+          LFI_TRY(core::launch_inv(af, st));
+        }
+        return LFI_OK;
+      };
+      // The frame chain is ~6 short, strictly dependent launches per frame.  LFI_SAMPLE_GRAPH=1 captures the whole chunk into
+      // ONE CUDA graph (every pointer and shape is fixed for the call).  Measured on B200 (1,024 sequences x 750 frames): 322.9 ms
+      // with and without the graph - the chain is bound by the kernels themselves, not by launch gaps - so it is off by default.
+      LFI_TRY(run_frames_graphed(frames, Tc, st));
       continue;
     }
     LFI_TRY(core::launch_inv(a, st));
@@ -1070,6 +1129,11 @@ int lfi_expand_faces(const float *x, const float *means, const float *stds, size
   LFI_REQUIRE(exp_dim >= 0 && jaw_dim >= 0 && neck_dim >= 0 && exp_dim <= 100 && jaw_dim <= 3 && neck_dim <= 3 && exp_dim + jaw_dim + neck_dim >= 1,
               LFI_ERR_SHAPE, "lfi_expand_faces: expression/jaw/neck = %d/%d/%d do not fit the 106-wide FLAME vector", exp_dim, jaw_dim, neck_dim);
   return aux::expand_faces(x, means, stds, rows, exp_dim, jaw_dim, neck_dim, out, (cudaStream_t)stream);
+}
+
+int lfi_gather_batch(const float *raw, const long long *row0, int B, int T, int dim, float *out, void *stream) {
+  LFI_REQUIRE(raw && row0 && out && B >= 1 && T >= 1 && dim >= 1, LFI_ERR_ARG, "lfi_gather_batch: bad argument");
+  return aux::gather_batch(raw, row0, B, T, dim, out, (cudaStream_t)stream);
 }
 
 int lfi_jerk(const float *x, int B, int T, int C, void *scratch8, float *out, void *stream) {

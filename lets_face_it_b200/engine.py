@@ -112,7 +112,10 @@ class Engine:
     # ------------------------------------------------------------------ flat storage
     def _layout(self):
         items = []  # (name, [params per step] or [param])
-        sb = (_STEP_BLOCKS_LU if self.LU else _STEP_BLOCKS_W) + _STEP_BLOCKS_F
+        # Order = the order in which the backward pass finishes the gradients: the flow-step weight blocks first (final before
+        # the encoder backward: the bucket that is all-reduced while the encoders run), then ActNorm / 1x1-conv and the encoder
+        # blocks (final only when the backward call returns) as ONE contiguous tail - a single trailing all-reduce.
+        sb = _STEP_BLOCKS_F + (_STEP_BLOCKS_LU if self.LU else _STEP_BLOCKS_W)
         for name, path in sb:
             if self.steps:
                 items.append((name, [_get(st, path) for st in self.steps]))

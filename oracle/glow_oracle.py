@@ -422,3 +422,28 @@ def derange_batch(batch, modalities, permutation):
         elif batch.get(m) is not None:
             out[m] = batch[m]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Input side; test infrastructure only.  The reference's MimicryDataset needs h5py and
+# pytorch_lightning, which are absent here, so this restatement is pinned by calling the SAME torch / random primitives the
+# reference calls (torch.arange(L).unfold(0, seq_len, 1), random.sample) rather than by running the class: parity for this
+# row is anchored on those call sites (mimicry_data_module.py:35-42, 44-78).
+def dataset_window_table(segments, seq_len, rng):
+    """MimicryDataset.__init__ (mimicry_data_module.py:33-42): [(segment key, [frame indices])], shuffled by random.sample."""
+    tmp = []
+    for key, seg in enumerate(segments):
+        L = len(seg["p1_face"])
+        if L >= seq_len:
+            for seq in torch.arange(L).unfold(0, seq_len, 1):
+                tmp.append((key, seq.int().tolist()))
+    return rng.sample(tmp, len(tmp))
+
+
+def dataset_batch(segments, table, index):
+    """__getitem__ (mimicry_data_module.py:44-78) for every item of `index`, stacked as the DataLoader's default collate does."""
+    out = {}
+    for m in MODALITIES:
+        if m in segments[0]:
+            out[m] = torch.stack([segments[table[i][0]][m][table[i][1]] for i in index])
+    return out

@@ -163,3 +163,39 @@ def test_oracle_three_optimizer_steps_match_reference_vectors():
         ref = torch.from_numpy(g["delta/" + n]).double()
         got = (P[n].detach() - theta0[n]).double().reshape(ref.shape)
         assert float((got - ref).norm()) <= 0.02 * float(ref.norm()) + 1e-12, n
+
+
+@pytest.mark.reference
+def test_reference_yaml_files_load_unchanged():
+    """The reference's own hparams files (code/glow_pytorch/hparams/*.yaml, 159 lines each) load through
+    `lets_face_it_b200.hparams.load_hparams` and build the drop-in SeqGlow; for final_model.yaml the result has exactly the
+    shapes of the packaged subset (authoring container only: the GPU box has no reference tree)."""
+    import os
+
+    from lets_face_it_b200.glow import SeqGlow
+    from lets_face_it_b200.hparams import load_hparams
+    from oracle.ref_shim import REF_YAML_DIR
+
+    ours = load_hparams()
+    for name in ("final_model.yaml", "no_face.yaml", "no_speech.yaml", "no_nll_trick.yaml"):
+        path = os.path.join(REF_YAML_DIR, name)
+        if not os.path.isfile(path):
+            continue
+        hp = load_hparams(path)
+        torch.manual_seed(0)
+        np.random.seed(0)
+        m = SeqGlow(hp)
+        assert m.feature_encoder.dim == hp.Conditioning["p1_face"]["dim"] * hp.Conditioning["p1_face"]["history"] + sum(
+            2 * hp.Conditioning[k]["hidden_dim"] for k in ("p2_face", "p1_speech", "p2_speech") if hp.Conditioning[k]["history"])
+        if name == "final_model.yaml":
+            for sec in ("Conditioning", "Glow", "Data"):
+                for k, v in getattr(ours, sec).items():
+                    ref = getattr(hp, sec)[k]
+                    if isinstance(v, dict):
+                        for kk, vv in v.items():
+                            assert ref[kk] == vv, (sec, k, kk)
+                    else:
+                        assert ref == v, (sec, k)
+            assert hp.lr == ours.lr and hp.gradient_clip_val == ours.gradient_clip_val and hp.batch_size == ours.batch_size
+            assert hp.Optim["args"]["adam"] == ours.Optim["args"]["adam"]
+            assert hp.Optim["Schedule"]["args"]["step"] == ours.Optim["Schedule"]["args"]["step"]
