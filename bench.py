@@ -432,6 +432,16 @@ def run_ours(a):
                     traffic = json.load(f).get(a.gemm, {}).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        step_traffic = None
+        sp = os.path.join(ROOT, "profiles", "r02_step_traffic_default.json")
+        if os.path.isfile(sp):
+            try:
+                with open(sp) as f:
+                    st_ = json.load(f)
+                step_traffic = {"dram_bytes_per_step": st_.get("step_dram_bytes"), "read": st_.get("step_dram_read"), "write": st_.get("step_dram_write"),
+                                "source": "ncu dram__bytes_read/write.sum summed over every kernel of one step (scripts/gpu_r2_traffic.sh, profiles/r02_step_traffic_default.json); not re-measured in this run"}
+            except Exception:
+                step_traffic = None
         products = 3 if a.gemm == "bf16x3" else 1
         out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst, "traffic": traffic,
                            "kernel": "tc::gemm_tc_kernel, cond_transform for all 16 steps [%d x %d x %d], mode %s" % (M, N, K, a.gemm),
@@ -440,6 +450,8 @@ def run_ours(a):
                            "mma_products_per_flop": products, "tensor_pipe_frac": ach * products / burst,
                            "note": "achieved = algorithmic 2MNK / CUDA-event time; the split-bf16 (bf16x3) parity mode issues 3 tcgen05 "
                                    "products per algorithmic product, so tensor_pipe_frac = 3 x frac is the tensor-pipe utilisation",
+                           "traffic_source": "ncu capture of this same stand-alone launch (profiles/roofline_traffic.json); not re-measured in this run",
+                           "step_traffic": step_traffic,
                            "step_frac_of_tensor_roofline": value / world * FLOP_PER_FRAME_TRAIN / 1e12 / sust}
         del A, W, C
 
