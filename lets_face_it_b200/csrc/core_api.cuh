@@ -18,6 +18,14 @@ struct Stash {
   float *xin;    // [.,C]   input of step k (k >= 1; slot k = K unused)
 };
 
+// tensor-core side of the hybrid wavefronts (zero = off)
+struct WaveTc {
+  int mode;                      // lfi_gemm_mode of the batched products (0 = off)
+  const void *whh_hi, *whh_lo;   // bf16 planes of W_hh [K][GH][H] (lo null in bf16 mode), split once per call
+  float *ghbuf;                  // [2][K][B][GH] products of two consecutive wavefronts (forward)
+  void *gws; size_t gws_bytes;   // operand-plane scratch of the GEMMs
+};
+
 struct FwdArgs {
   Dims d;
   DerivedView dv;
@@ -43,6 +51,11 @@ struct FwdArgs {
   // the thread-per-sequence stores of that kernel contiguous; the backward pipeline reads the same layout
   int stash_tiled;
   int g_tiled;  // 1: G is row-interleaved (core_pipe.cuh: g_tiled_off with ld = g_ld), tensor-core pipeline only
+  // Hybrid wavefronts (tensor-core GEMM modes, shapes the stage pipelines do not cover - e.g. the wide variant K = 32, H = 256,
+  // LSTM): the recurrent product h[k][t-1] W_hh[k]^T of every cell of a wavefront is ONE batched tcgen05 GEMM issued before the
+  // wavefront's launch (core_fwd.cu: launch_fwd_t), and the cell kernel adds the result instead of streaming W_hh through FFMA.
+  WaveTc wtc;
+  const float *gh_pre;        // set per wavefront by the launcher: [K][B][GH] products of this wavefront's cells (cells with t >= 1)
 };
 
 struct InvArgs {
@@ -95,6 +108,10 @@ struct BwdArgs {
   float *dx0_out;             // [B][C]  dL/d(input of the step)
   float *dh0_out, *dc0_out;   // [B][H]  dL/d(h_in), dL/d(c_in)
   long dg_ld; int dg_k0;      // dG row pitch / first step (0: K*GH, 0)
+  // hybrid wavefronts (see FwdArgs): dh[k][t-1] += dA_h[k][t] W_hh[k] as one batched tcgen05 GEMM behind every wavefront launch;
+  // the cell kernel then leaves that product out (skip_hh set by the launcher)
+  WaveTc wtc;
+  int skip_hh;
 };
 
 int fwd_smem_bytes(const Dims &d, int R);

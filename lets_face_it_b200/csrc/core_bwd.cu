@@ -194,8 +194,9 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
     }
 
   // ---- I. dh_prev += dA_h @ W_hh ;  J. dz1 += dA_i @ W_ih[:, :Ci] ----------------------------------
-  tile_gemm<RPT>(dact, w.Whh, H, GH, H, sm + sp.wst, [&](int r, int j, float v) { dhr[r * pH + j] += v; },
-                 gru ? 2 * H : (1 << 30), gru ? H : 0, 0);
+  if (!a.skip_hh)  // (hybrid wavefronts: this product is the batched tcgen05 GEMM behind the launch, accumulated into a.dh)
+    tile_gemm<RPT>(dact, w.Whh, H, GH, H, sm + sp.wst, [&](int r, int j, float v) { dhr[r * pH + j] += v; },
+                   gru ? 2 * H : (1 << 30), gru ? H : 0, 0);
   tile_gemm<RPT>(dact, w.WihZ, d.Cip, GH, Ci, sm + sp.wst, [&](int r, int j, float v) { zrow[r * pC + j] += v; });
   __syncthreads();
   if (t > 0)
@@ -246,10 +247,25 @@ template <int RPT> static int launch_bwd_t(const BwdArgs &a, cudaStream_t st) {
   const int bytes = plan_smem(a.d, R, true, false).total * (int)sizeof(float);
   LFI_CUDA(cudaFuncSetAttribute(core_bwd_wave<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   const int tiles = (a.B + R - 1) / R, K = a.d.K;
+  const bool tcw = a.wtc.mode != 0 && a.single < 0;
+  BwdArgs aw = a;
+  aw.skip_hh = tcw ? 1 : 0;
   for (int wave = a.Tp + K - 2; wave >= 0; --wave) {
     const int k0 = max(0, wave - a.Tp + 1), k1 = min(K - 1, wave);
     dim3 grid(tiles, k1 - k0 + 1);
-    core_bwd_wave<RPT><<<grid, NT, bytes, st>>>(a, wave, k0);
+    core_bwd_wave<RPT><<<grid, NT, bytes, st>>>(aw, wave, k0);
+    if (!tcw) continue;
+    // cells (k, t = wave - k) with t >= 1 wrote the direct part of d h[k][t-1] into a.dh[k][t]; add dA_h[k][t] W_hh[k]  (batch over k)
+    const int kb0 = k0, kb1 = min(k1, wave - 1);
+    if (kb1 >= kb0) {
+      const int H = a.d.H, GH = a.d.GH, B = a.B, Tp = a.Tp;
+      const size_t cell0 = (size_t)kb0 * Tp + (wave - kb0);     // (k, t) of the first cell; next cell: + (Tp - 1)
+      GemmArgs q = gemm_args(0, 0, B, H, GH, a.dAh + cell0 * B * GH, GH, nullptr, H, a.dh + cell0 * B * H, H, LFI_EPI_ACCUM);
+      q.batch = kb1 - kb0 + 1; q.sA = (long)(Tp - 1) * B * GH; q.sB = (long)GH * H; q.sC = (long)(Tp - 1) * B * H;
+      q.pB = plane_ref((const uint16_t *)a.wtc.whh_hi + (size_t)kb0 * GH * H,
+                       a.wtc.whh_lo ? (const uint16_t *)a.wtc.whh_lo + (size_t)kb0 * GH * H : nullptr, H, (long)GH * H);
+      LFI_TRY(gemm_dispatch(a.wtc.mode, q, a.wtc.gws, a.wtc.gws_bytes, st));
+    }
   }
   LFI_LAUNCH_CHECK_N(a.Tp + K - 1);
   return LFI_OK;

@@ -23,7 +23,7 @@ namespace core {
 template <int RPT>
 __device__ __forceinline__ void coupling_net(const Dims &d, const StepWeights &w, const SmemPlan &sp, float *sm,
                                              int nrows, const float *Grow, long g_ld, float *st_gates, float *st_ahn,
-                                             float *st_h, float *st_c, float *st_o) {
+                                             float *st_h, float *st_c, float *st_o, bool hh_pre = false, const float *gh_rows = nullptr) {
   constexpr int R = Tile<RPT>::R, RS = Tile<RPT>::RS;
   const int tid = threadIdx.x;
   const int H = d.H, GH = d.GH, pS = odd(GH), pH = odd(H), pO = odd(d.Co > d.C ? d.Co : d.C);
@@ -36,11 +36,22 @@ __device__ __forceinline__ void coupling_net(const Dims &d, const StepWeights &w
   });
   // h part
   const bool gru = d.G == 3;
-  tile_gemm<RPT>(hp, w.WhhT, GH, H, GH, sm + sp.wst, [&](int r, int j, float v) {
-    v += w.b_hh[j];
-    if (gru && j >= 2 * H) ahn[r * pH + (j - 2 * H)] = v;
-    else S[r * pS + j] += v;
-  });
+  if (!hh_pre) {
+    tile_gemm<RPT>(hp, w.WhhT, GH, H, GH, sm + sp.wst, [&](int r, int j, float v) {
+      v += w.b_hh[j];
+      if (gru && j >= 2 * H) ahn[r * pH + (j - 2 * H)] = v;
+      else S[r * pS + j] += v;
+    });
+  } else {  // hybrid wavefront: the product came from the batched tcgen05 GEMM (gh_rows == nullptr: zero state, t = 0)
+    __syncthreads();  // S was written by other threads in the z1 epilogue
+    for (int e = tid; e < R * GH; e += NT) {
+      const int r = e / GH, j = e - r * GH;
+      float v = w.b_hh[j];
+      if (gh_rows && r < nrows) v += gh_rows[(size_t)r * GH + j];
+      if (gru && j >= 2 * H) ahn[r * pH + (j - 2 * H)] = v;
+      else S[r * pS + j] += v;
+    }
+  }
   __syncthreads();
   // gate math: lanes along rows
   for (int e = tid; e < R * H; e += NT) {
@@ -138,7 +149,8 @@ __global__ void __launch_bounds__(NT) core_fwd_wave(FwdArgs a, int wave, int kmi
   coupling_net<RPT>(d, w, sp, sm, nrows, a.G + ((size_t)t * B + row0) * a.g_ld + (size_t)(k - a.g_k0) * d.GH, a.g_ld,
                     a.st_gates ? a.st_gates + rowbase * d.GH : nullptr, a.st_ahn ? a.st_ahn + rowbase * H : nullptr,
                     a.st_h + rowbase * H, a.st_c ? a.st_c + rowbase * H : nullptr,
-                    a.st_o ? a.st_o + rowbase * d.Co : nullptr);
+                    a.st_o ? a.st_o + rowbase * d.Co : nullptr, a.gh_pre != nullptr,
+                    (a.gh_pre && t > 0) ? a.gh_pre + ((size_t)k * B + row0) * d.GH : nullptr);
 
   // 4. coupling (models.py:331-341), log-det, NLL on the last step (modules.py:207-212, models.py:563-565)
   const float *orow = sm + sp.orow;
@@ -323,11 +335,30 @@ template <int RPT> static int launch_fwd_t(const FwdArgs &a, cudaStream_t st) {
   LFI_CUDA(cudaFuncSetAttribute(core_fwd_wave<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   const int tiles = (a.B + R - 1) / R;
   const int nk = a.k_last - a.k_first + 1;
+  const bool tcw = a.wtc.mode != 0 && a.k_first == 0 && !a.h0 && !a.c0;  // hybrid wavefronts: whole-sequence training forward only
   for (int wave = 0; wave < a.Tp + nk - 1; ++wave) {
     // active steps: k_first + i with 0 <= wave - i < Tp
     const int i0 = max(0, wave - a.Tp + 1), i1 = min(nk - 1, wave);
     dim3 grid(tiles, i1 - i0 + 1);
-    core_fwd_wave<RPT><<<grid, NT, bytes, st>>>(a, wave + a.k_first, a.k_first + i0);
+    if (!tcw) {
+      core_fwd_wave<RPT><<<grid, NT, bytes, st>>>(a, wave + a.k_first, a.k_first + i0);
+      continue;
+    }
+    FwdArgs aw = a;
+    float *gh = a.wtc.ghbuf + (size_t)(wave & 1) * a.d.K * a.B * a.d.GH;
+    aw.gh_pre = gh;
+    // cells (k, t = wave - k) with t >= 1: k in [i0, min(i1, wave - 1)];  gh[k] = h[k][t-1] W_hh[k]^T   (batch over k)
+    const int kb0 = i0, kb1 = min(i1, wave - 1);
+    if (kb1 >= kb0) {
+      const int H = a.d.H, GH = a.d.GH, B = a.B, Tp = a.Tp;
+      const size_t cellA = (size_t)kb0 * Tp + (wave - kb0 - 1);   // (k, t-1) of the first cell; next cell: + (Tp - 1)
+      GemmArgs q = gemm_args(0, 1, B, GH, H, a.st_h + cellA * B * H, H, nullptr, H, gh + (size_t)kb0 * B * GH, GH, 0);
+      q.batch = kb1 - kb0 + 1; q.sA = (long)(Tp - 1) * B * H; q.sB = (long)GH * H; q.sC = (long)B * GH;
+      q.pB = plane_ref((const uint16_t *)a.wtc.whh_hi + (size_t)kb0 * GH * H,
+                       a.wtc.whh_lo ? (const uint16_t *)a.wtc.whh_lo + (size_t)kb0 * GH * H : nullptr, H, (long)GH * H);
+      LFI_TRY(gemm_dispatch(a.wtc.mode, q, a.wtc.gws, a.wtc.gws_bytes, st));
+    }
+    core_fwd_wave<RPT><<<grid, NT, bytes, st>>>(aw, wave, i0);
   }
   LFI_LAUNCH_CHECK_N(a.Tp + nk - 1);
   return LFI_OK;

@@ -133,6 +133,10 @@ struct TrainWs {
   // written by their producers (GEMM epilogues, core kernels), never re-split
   bool cp, cp_lo;
   bool st_tiled;  // gates / ahn / h stash in the tiled layout of the tensor-core flow-core pipeline
+  // hybrid wavefronts (shapes outside the stage pipelines, tensor-core modes): W_hh planes [K][GH][H] and the per-wavefront products
+  bool wave_tc;
+  void *wt_hi, *wt_lo;
+  float *ghbuf;
   void *cact_hi, *cact_lo, *y_hi, *y_lo, *zf_hi, *zf_lo, *h_hi, *h_lo;
   void *dG_hi, *dG_lo, *dAh_hi, *dAh_lo, *dO_hi, *dO_lo, *dzf_hi, *dzf_lo, *dC_hi, *dC_lo;
   size_t bytes;
@@ -191,6 +195,14 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
   w->gh = b.take<float>(ghmax);
   const size_t cells = K * M;
   w->st_tiled = w->cp && core::pipe_tc_supported(d, d.K);
+  w->wave_tc = mode != LFI_GEMM_FP32 && !core::pipe_supported(d, d.K, false) && d.H % 8 == 0 && d.GH % 16 == 0 && B >= 16 &&
+               env_flag("LFI_WAVE_TC", true);
+  w->wt_hi = w->wt_lo = nullptr; w->ghbuf = nullptr;
+  if (w->wave_tc) {
+    w->wt_hi = take_bf16(b, K * d.GH * d.H);
+    w->wt_lo = mode == LFI_GEMM_BF16X3 ? take_bf16(b, K * d.GH * d.H) : nullptr;
+    w->ghbuf = b.take<float>(2 * K * (size_t)B * d.GH);
+  }
   const size_t cells_t = w->st_tiled ? K * Tp * round_up_sz((size_t)B, 64) : cells;  // tiled stash: whole 64-sequence tiles
   w->st.y = b.take<float>(cells * d.C);
   w->st.zf = b.take<float>(cells * d.C);
@@ -536,6 +548,10 @@ int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params 
   if (w.cp) { a.py_hi = w.y_hi; a.py_lo = w.y_lo; a.pzf_hi = w.zf_hi; a.pzf_lo = w.zf_lo; a.ph_hi = w.h_hi; a.ph_lo = w.h_lo; }
   a.stash_tiled = w.st_tiled ? 1 : 0;
   a.g_tiled = w.st_tiled ? 1 : 0;
+  if (w.wave_tc) {  // recurrent weights as operand planes, once per call (they change with every optimizer step)
+    LFI_TRY(split_to_planes(p->w_hh, d.GH, d.H, d.H, (long)d.GH * d.H, d.K, w.wt_hi, w.wt_lo, st));
+    a.wtc.mode = gemm_mode; a.wtc.whh_hi = w.wt_hi; a.wtc.whh_lo = w.wt_lo; a.wtc.ghbuf = w.ghbuf; a.wtc.gws = gws; a.wtc.gws_bytes = gws_bytes;
+  }
   return core::launch_fwd(a, st);
 }
 
@@ -575,6 +591,9 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
     a.g_b_ih = g->b_ih;
   }
   a.stash_tiled = w.st_tiled ? 1 : 0;
+  if (w.wave_tc) {  // planes of W_hh were built by the forward call of this step
+    a.wtc.mode = gemm_mode; a.wtc.whh_hi = w.wt_hi; a.wtc.whh_lo = w.wt_lo; a.wtc.ghbuf = w.ghbuf; a.wtc.gws = gws; a.wtc.gws_bytes = gws_bytes;
+  }
   LFI_TRY(core::launch_bwd(a, st));
 
   // 2. weight gradients of the per-step matrices as batched (over k) reductions over the M rows.  With every operand in

@@ -235,3 +235,42 @@ def test_wide_variant_matches_oracle(rnn):
             ref = P[n].grad.double()
             worst = max(worst, float((v.double().cpu().reshape(ref.shape) - ref).norm() / ref.norm().clamp_min(1e-30)))
         assert worst < gtol, (mode, worst)
+
+
+@pytest.mark.parametrize("rnn,H,K,B", [("lstm", 64, 3, 40), ("gru", 192, 5, 70)])
+def test_hybrid_wavefronts_match_ffma_wavefronts_and_oracle(rnn, H, K, B):
+    """Shapes outside the stage pipelines (LSTM, H != 128) in the tensor-core modes: the recurrent products of every wavefront
+    run as ONE batched tcgen05 GEMM (forward h W_hh^T, backward dA_h W_hh) and the cell kernels skip them (LFI_WAVE_TC=1, the
+    default) - against the all-FFMA wavefront kernels (LFI_WAVE_TC=0) and the oracle.  Ragged batches (B not a multiple of the
+    128-row GEMM tile or of the cell tile)."""
+    import copy
+
+    from lets_face_it_b200 import _cabi as cabi
+
+    hp = copy.deepcopy(final_hparams())
+    hp.Glow["K"] = K
+    hp.Glow["hidden_channels"] = H
+    hp.Glow["rnn_type"] = rnn
+    hy = O.Hyper.from_hparams(hp)
+    m = build_kat_model(hp)
+    m.glow.set_actnorm_init(True)
+    P = O.clone_params(oracle_params_from(m), requires_grad=True)
+    T = 30
+    batch = kat_batch(hp, B, T, seed=43)
+    z_ref, nll_ref, loss_ref = O.seq_forward(P, hy, batch)
+    loss_ref.backward()
+    m = m.to(DEV).train()
+    m.gemm_mode = cabi.GEMM_BF16X3
+    dbatch = to_device(batch, DEV)
+    z1, n1, g1 = _fwd_bwd(m, dbatch)
+    with _env(LFI_WAVE_TC="0"):
+        z0, n0, g0 = _fwd_bwd(m, dbatch)
+    assert relerr(z1, z0) < 2e-5 and relerr(n1, n0) < 1e-5
+    assert relerr(z1, z_ref.detach()) < 1e-4 and relerr(n1, nll_ref.detach()) < 1e-4
+    for k_ in g0:
+        ref = g0[k_].double()
+        err = float((g1[k_].double() - ref).norm() / ref.norm().clamp_min(1e-30))
+        assert err < 2e-3, (k_, err)
+        oref = P[k_].grad.double()
+        oerr = float((g1[k_].double().cpu().reshape(oref.shape) - oref).norm() / oref.norm().clamp_min(1e-30))
+        assert oerr < 5e-3, (k_, oerr)
