@@ -372,7 +372,8 @@ def run_ours(a):
         sample = {"value": Bs * Tg * world / (ms_s * 1e-3), "unit": "frames/s", "sequences_per_gpu": Bs, "frames_per_sequence": Tg, "eps": 0.7,
                   "ms": ms_s, "gpu_launches": int(L.lfi_launch_count() - n0),
                   "note": "SeqGlow.inference, zero seed frames, temperature 0.7; per frame: AR window gather, two tcgen05 conditioning "
-                          "GEMMs, one launch walking the 16 inverse steps - captured as one CUDA graph per chunk of frames; no collective",
+                          "GEMMs, one launch walking the 16 inverse steps, all stream-ordered with no host round trip inside the call (LFI_SAMPLE_GRAPH=1 "
+                          "captures the chain as a CUDA graph per chunk: measured no gain, the chain is kernel bound); no collective",
                   # the sampler is a strictly serial chain per sequence (16 inverse steps x 750 frames): latency bound, reported as the
                   # critical path per frame next to the tensor roofline of its contractions (42.38 MFLOP per frame and sequence)
                   "roofline": {"bound": "latency", "us_per_frame": 1e3 * ms_s / Tg, "us_per_inverse_step": 1e3 * ms_s / Tg / hy.K,
@@ -444,6 +445,8 @@ def run_ours(a):
             except Exception:
                 step_traffic = None
         products = 3 if a.gemm == "bf16x3" else 1
+        # canonical training FLOP per frame and sequence: final 127.15 M; wide (K=32, H=256) LSTM 306.6 M, GRU 267.5 M
+        flop_frame = {"final": FLOP_PER_FRAME_TRAIN, "wide-lstm": 6.0 * 51102208, "wide-gru": 6.0 * 44581376}[a.variant]
         out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst, "traffic": traffic,
                            "kernel": "tc::gemm_tc_kernel, cond_transform for all 16 steps [%d x %d x %d], mode %s" % (M, N, K, a.gemm),
                            "peak_source": how + " (burst: kernel timed alone)",
@@ -453,7 +456,8 @@ def run_ours(a):
                                    "products per algorithmic product, so tensor_pipe_frac = 3 x frac is the tensor-pipe utilisation",
                            "traffic_source": "ncu capture of this same stand-alone launch (profiles/roofline_traffic.json); not re-measured in this run",
                            "step_traffic": step_traffic,
-                           "step_frac_of_tensor_roofline": value / world * FLOP_PER_FRAME_TRAIN / 1e12 / sust}
+                           "step_flop_per_frame": flop_frame,
+                           "step_frac_of_tensor_roofline": value / world * flop_frame / 1e12 / sust}
         del A, W, C
 
         # ---- secondary: split-bf16 forward and flow core (z / NLL unchanged), single bf16 products in the backward GEMMs ---------
