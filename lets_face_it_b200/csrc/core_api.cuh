@@ -116,6 +116,7 @@ struct BwdArgs {
 
 int fwd_smem_bytes(const Dims &d, int R);
 int choose_rpt(const Dims &d, int B, bool bwd, bool sampler);
+int choose_tile(const Dims &d, int B, bool bwd, bool sampler, int *kc_out);  // + weight-ring depth (16 or 8 rows per stage)
 int launch_fwd(const FwdArgs &a, cudaStream_t st);
 int launch_inv(const InvArgs &a, cudaStream_t st);
 int launch_bwd(const BwdArgs &a, cudaStream_t st);

@@ -9,7 +9,7 @@
 namespace lfi {
 namespace core {
 
-template <int RPT>
+template <int RPT, int KC>
 __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmin) {
   extern __shared__ __align__(16) float sm[];
   constexpr int R = Tile<RPT>::R, RS = Tile<RPT>::RS;
@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
   const int row0 = blockIdx.x * R, nrows = min(R, a.B - row0);
   const int C = d.C, Ci = d.Ci, Cz = d.Cz, Co = d.Co, H = d.H, GH = d.GH, B = a.B, Tp = a.Tp;
   const bool gru = d.G == 3;
-  const SmemPlan sp = plan_smem(d, R, true, false);
+  const SmemPlan sp = plan_smem(d, R, true, false, KC);
   const StepWeights w = a.dv.step(d, k);
   const size_t cell = (size_t)k * Tp + t;
   const int pC = odd(C), pO = odd(Co > C ? Co : C), pS = odd(GH), pH = odd(H);
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
   }
 
   // ---- E. dh = dlin @ Wf (+ dh from the next frame) ------------------------------------------------
-  tile_gemm<RPT>(xs, w.Wf, H, Co, H, sm + sp.wst, [&](int r, int j, float v) {
+  tile_gemm<RPT, KC>(xs, w.Wf, H, Co, H, sm + sp.wst, [&](int r, int j, float v) {
     if (r < nrows) {
       if (a.single >= 0) { if (a.dh_ext) v += a.dh_ext[(size_t)(row0 + r) * H + j]; }
       else if (t < Tp - 1) v += a.dh[((cell + 1) * B + row0 + r) * H + j];
@@ -195,9 +195,10 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
 
   // ---- I. dh_prev += dA_h @ W_hh ;  J. dz1 += dA_i @ W_ih[:, :Ci] ----------------------------------
   if (!a.skip_hh)  // (hybrid wavefronts: this product is the batched tcgen05 GEMM behind the launch, accumulated into a.dh)
-    tile_gemm<RPT>(dact, w.Whh, H, GH, H, sm + sp.wst, [&](int r, int j, float v) { dhr[r * pH + j] += v; },
+    tile_gemm<RPT, KC>(dact, w.Whh, H, GH, H, sm + sp.wst, [&](int r, int j, float v) { dhr[r * pH + j] += v; },
                    gru ? 2 * H : (1 << 30), gru ? H : 0, 0);
-  tile_gemm<RPT>(dact, w.WihZ, d.Cip, GH, Ci, sm + sp.wst, [&](int r, int j, float v) { zrow[r * pC + j] += v; });
+  if (Ci <= 64) skinny_gemm<RPT>(dact, w.WihZ, d.Cip, GH, Ci, sm + sp.wst, [&](int r, int j, float v) { zrow[r * pC + j] += v; });
+  else tile_gemm<RPT, KC>(dact, w.WihZ, d.Cip, GH, Ci, sm + sp.wst, [&](int r, int j, float v) { zrow[r * pC + j] += v; });
   __syncthreads();
   if (t > 0)
     for (int e = tid; e < nrows * H; e += NT) {
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
   }
 
   // ---- K. dy = dzf @ W^T ; ActNorm backward (modules.py:45-66) --------------------------------------
-  tile_gemm<RPT>(zact, w.WT, d.Cp, C, C, sm + sp.wst, [&](int r, int j, float dy) {
+  tile_gemm<RPT, KC>(zact, w.WT, d.Cp, C, C, sm + sp.wst, [&](int r, int j, float dy) {
     const float y = (r < nrows) ? a.st.y[(cell * B + row0 + r) * C + j] : 0.f;
     dxr[r * pC + j] = dy * expf(w.an_logs[j]);
     prod[r * pO + j] = dy * y;
@@ -242,10 +243,10 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
   }
 }
 
-template <int RPT> static int launch_bwd_t(const BwdArgs &a, cudaStream_t st) {
+template <int RPT, int KC> static int launch_bwd_t(const BwdArgs &a, cudaStream_t st) {
   constexpr int R = Tile<RPT>::R;
-  const int bytes = plan_smem(a.d, R, true, false).total * (int)sizeof(float);
-  LFI_CUDA(cudaFuncSetAttribute(core_bwd_wave<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  const int bytes = plan_smem(a.d, R, true, false, KC).total * (int)sizeof(float);
+  LFI_CUDA(cudaFuncSetAttribute(core_bwd_wave<RPT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   const int tiles = (a.B + R - 1) / R, K = a.d.K;
   const bool tcw = a.wtc.mode != 0 && a.single < 0;
   BwdArgs aw = a;
@@ -253,7 +254,7 @@ template <int RPT> static int launch_bwd_t(const BwdArgs &a, cudaStream_t st) {
   for (int wave = a.Tp + K - 2; wave >= 0; --wave) {
     const int k0 = max(0, wave - a.Tp + 1), k1 = min(K - 1, wave);
     dim3 grid(tiles, k1 - k0 + 1);
-    core_bwd_wave<RPT><<<grid, NT, bytes, st>>>(aw, wave, k0);
+    core_bwd_wave<RPT, KC><<<grid, NT, bytes, st>>>(aw, wave, k0);
     if (!tcw) continue;
     // cells (k, t = wave - k) with t >= 1 wrote the direct part of d h[k][t-1] into a.dh[k][t]; add dA_h[k][t] W_hh[k]  (batch over k)
     const int kb0 = k0, kb1 = min(k1, wave - 1);
@@ -271,23 +272,28 @@ template <int RPT> static int launch_bwd_t(const BwdArgs &a, cudaStream_t st) {
   return LFI_OK;
 }
 
-template <int RPT> static int launch_bwd_single_t(const BwdArgs &a, cudaStream_t st) {
+template <int RPT, int KC> static int launch_bwd_single_t(const BwdArgs &a, cudaStream_t st) {
   constexpr int R = Tile<RPT>::R;
-  const int bytes = plan_smem(a.d, R, true, false).total * (int)sizeof(float);
-  LFI_CUDA(cudaFuncSetAttribute(core_bwd_wave<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  core_bwd_wave<RPT><<<dim3((a.B + R - 1) / R, 1), NT, bytes, st>>>(a, a.single, a.single);  // wave = k: t = 0
+  const int bytes = plan_smem(a.d, R, true, false, KC).total * (int)sizeof(float);
+  LFI_CUDA(cudaFuncSetAttribute(core_bwd_wave<RPT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  core_bwd_wave<RPT, KC><<<dim3((a.B + R - 1) / R, 1), NT, bytes, st>>>(a, a.single, a.single);  // wave = k: t = 0
   LFI_LAUNCH_CHECK();
   return LFI_OK;
 }
 
 int launch_bwd_single(const BwdArgs &a, cudaStream_t st) {
   LFI_REQUIRE(a.single >= 0 && a.single < a.d.K && a.Tp == 1 && a.dz_ext, LFI_ERR_ARG, "flow core backward (single cell): bad arguments");
-  const int rpt = choose_rpt(a.d, a.B, true, false);
-  switch (rpt) {
-    case 8: return launch_bwd_single_t<8>(a, st);
-    case 4: return launch_bwd_single_t<4>(a, st);
-    case 2: return launch_bwd_single_t<2>(a, st);
-    case 1: return launch_bwd_single_t<1>(a, st);
+  int kc = KC16;
+  const int rpt = choose_tile(a.d, a.B, true, false, &kc);
+  switch (rpt * 100 + kc) {
+    case 816: return launch_bwd_single_t<8, 16>(a, st);
+    case 416: return launch_bwd_single_t<4, 16>(a, st);
+    case 216: return launch_bwd_single_t<2, 16>(a, st);
+    case 116: return launch_bwd_single_t<1, 16>(a, st);
+    case 808: return launch_bwd_single_t<8, 8>(a, st);
+    case 408: return launch_bwd_single_t<4, 8>(a, st);
+    case 208: return launch_bwd_single_t<2, 8>(a, st);
+    case 108: return launch_bwd_single_t<1, 8>(a, st);
   }
   set_error("flow core backward: shape does not fit shared memory (H=%d G=%d C=%d)", a.d.H, a.d.G, a.d.C);
   return LFI_ERR_SHAPE;
@@ -298,12 +304,17 @@ int launch_bwd(const BwdArgs &a, cudaStream_t st) {
     if (a.stash_tiled && a.pdG_hi && pipe_bwd_tc_supported(a.d)) return launch_bwd_pipe_tc(a, st);  // tensor-core GEMM modes
     return launch_bwd_pipe(a, st);
   }
-  const int rpt = choose_rpt(a.d, a.B, true, false);
-  switch (rpt) {
-    case 8: return launch_bwd_t<8>(a, st);
-    case 4: return launch_bwd_t<4>(a, st);
-    case 2: return launch_bwd_t<2>(a, st);
-    case 1: return launch_bwd_t<1>(a, st);
+  int kc = KC16;
+  const int rpt = choose_tile(a.d, a.B, true, false, &kc);
+  switch (rpt * 100 + kc) {
+    case 816: return launch_bwd_t<8, 16>(a, st);
+    case 416: return launch_bwd_t<4, 16>(a, st);
+    case 216: return launch_bwd_t<2, 16>(a, st);
+    case 116: return launch_bwd_t<1, 16>(a, st);
+    case 808: return launch_bwd_t<8, 8>(a, st);
+    case 408: return launch_bwd_t<4, 8>(a, st);
+    case 208: return launch_bwd_t<2, 8>(a, st);
+    case 108: return launch_bwd_t<1, 8>(a, st);
   }
   set_error("flow core backward: shape does not fit shared memory (H=%d G=%d C=%d)", a.d.H, a.d.G, a.d.C);
   return LFI_ERR_SHAPE;

@@ -20,7 +20,7 @@ namespace core {
 // in : sm[zact] rows [0,Ci) = z1 (act layout), sm[hp] = h_prev, sm[cp] = c_prev (LSTM)
 //      Grow != nullptr: S = G[row] (+ z1 part + h part);  else S already holds b_ih + c @ W_ih[:, Ci:]^T
 // out: sm[hp] = h_new, sm[cp] = c_new, sm[orow] = o; optional stashes
-template <int RPT>
+template <int RPT, int KC = KC16>
 __device__ __forceinline__ void coupling_net(const Dims &d, const StepWeights &w, const SmemPlan &sp, float *sm,
                                              int nrows, const float *Grow, long g_ld, float *st_gates, float *st_ahn,
                                              float *st_h, float *st_c, float *st_o, bool hh_pre = false, const float *gh_rows = nullptr) {
@@ -30,14 +30,14 @@ __device__ __forceinline__ void coupling_net(const Dims &d, const StepWeights &w
   float *S = sm + sp.S, *ahn = sm + sp.ahn, *hp = sm + sp.hp, *cp = sm + sp.cp, *orow = sm + sp.orow;
 
   // z1 part (and G init)
-  tile_gemm<RPT>(sm + sp.zact, w.WzT, GH, d.Ci, GH, sm + sp.wst, [&](int r, int j, float v) {
+  tile_gemm<RPT, KC>(sm + sp.zact, w.WzT, GH, d.Ci, GH, sm + sp.wst, [&](int r, int j, float v) {
     if (Grow) S[r * pS + j] = v + (r < nrows ? Grow[(size_t)r * g_ld + j] : 0.f);
     else S[r * pS + j] += v;
   });
   // h part
   const bool gru = d.G == 3;
   if (!hh_pre) {
-    tile_gemm<RPT>(hp, w.WhhT, GH, H, GH, sm + sp.wst, [&](int r, int j, float v) {
+    tile_gemm<RPT, KC>(hp, w.WhhT, GH, H, GH, sm + sp.wst, [&](int r, int j, float v) {
       v += w.b_hh[j];
       if (gru && j >= 2 * H) ahn[r * pH + (j - 2 * H)] = v;
       else S[r * pS + j] += v;
@@ -82,16 +82,21 @@ __device__ __forceinline__ void coupling_net(const Dims &d, const StepWeights &w
   if (st_c && !gru)
     for (int e = tid; e < nrows * H; e += NT) { const int r = e / H, j = e - r * H; st_c[(size_t)r * H + j] = cp[j * RS + r]; }
   // LinearZeros (modules.py:93-95)
-  tile_gemm<RPT>(hp, w.WfT, d.Cop, H, d.Co, sm + sp.wst, [&](int r, int j, float v) {
-    orow[r * pO + j] = (v + w.bf[j]) * expf(3.0f * w.lf[j]);
-  });
+  if (d.Co <= 64)
+    skinny_gemm<RPT>(hp, w.WfT, d.Cop, H, d.Co, sm + sp.wst, [&](int r, int j, float v) {
+      orow[r * pO + j] = (v + w.bf[j]) * expf(3.0f * w.lf[j]);
+    });
+  else
+    tile_gemm<RPT, KC>(hp, w.WfT, d.Cop, H, d.Co, sm + sp.wst, [&](int r, int j, float v) {
+      orow[r * pO + j] = (v + w.bf[j]) * expf(3.0f * w.lf[j]);
+    });
   __syncthreads();
   if (st_o)
     for (int e = tid; e < nrows * d.Co; e += NT) { const int r = e / d.Co, j = e - r * d.Co; st_o[(size_t)r * d.Co + j] = orow[r * pO + j]; }
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int RPT>
+template <int RPT, int KC>
 __global__ void __launch_bounds__(NT) core_fwd_wave(FwdArgs a, int wave, int kmin) {
   extern __shared__ __align__(16) float sm[];
   constexpr int R = Tile<RPT>::R, RS = Tile<RPT>::RS;
@@ -100,7 +105,7 @@ __global__ void __launch_bounds__(NT) core_fwd_wave(FwdArgs a, int wave, int kmi
   const int k = kmin + blockIdx.y, t = wave - k;
   const int row0 = blockIdx.x * R, nrows = min(R, a.B - row0);
   const int C = d.C, Ci = d.Ci, Cz = d.Cz, H = d.H, B = a.B;
-  const SmemPlan sp = plan_smem(d, R, false, false);
+  const SmemPlan sp = plan_smem(d, R, false, false, KC);
   const StepWeights w = a.dv.step(d, k);
   const size_t cell = (size_t)k * a.Tp + t;
   const int pC = odd(C), pO = odd(d.Co > C ? d.Co : C);
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(NT) core_fwd_wave(FwdArgs a, int wave, int kmi
     if (d.G == 4) cp[m * RS + r] = cv;
   }
   // 2. invertible 1x1 conv (modules.py:186): z = y @ W
-  tile_gemm<RPT>(xs, w.Wfwd, d.Cp, C, C, sm + sp.wst, [&](int r, int j, float v) {
+  tile_gemm<RPT, KC>(xs, w.Wfwd, d.Cp, C, C, sm + sp.wst, [&](int r, int j, float v) {
     zrow[r * pC + j] = v;
     if (j < Ci) zact[j * RS + r] = v;
   });
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(NT) core_fwd_wave(FwdArgs a, int wave, int kmi
 
   // 3. coupling network
   const size_t rowbase = cell * B + row0;
-  coupling_net<RPT>(d, w, sp, sm, nrows, a.G + ((size_t)t * B + row0) * a.g_ld + (size_t)(k - a.g_k0) * d.GH, a.g_ld,
+  coupling_net<RPT, KC>(d, w, sp, sm, nrows, a.G + ((size_t)t * B + row0) * a.g_ld + (size_t)(k - a.g_k0) * d.GH, a.g_ld,
                     a.st_gates ? a.st_gates + rowbase * d.GH : nullptr, a.st_ahn ? a.st_ahn + rowbase * H : nullptr,
                     a.st_h + rowbase * H, a.st_c ? a.st_c + rowbase * H : nullptr,
                     a.st_o ? a.st_o + rowbase * d.Co : nullptr, a.gh_pre != nullptr,
@@ -311,28 +316,35 @@ constexpr int kMaxSmem = 227 * 1024;
 int fwd_smem_bytes(const Dims &d, int R) { return plan_smem(d, R, false, false).total * (int)sizeof(float); }
 
 // Rows per CTA = 4*RPT.  Larger tiles amortise the weight stream, smaller tiles expose more CTAs;
-// take the largest tile that still gives every SM a CTA (LFI_RPT overrides for experiments).
-int choose_rpt(const Dims &d, int B, bool bwd, bool sampler) {
+// take the largest tile that still gives every SM a CTA (LFI_RPT overrides for experiments).  The wavefront cell kernels
+// may also halve the weight ring (kc = 8) when that is what lets a tile fit (wide shapes: H = 256, LSTM).
+int choose_tile(const Dims &d, int B, bool bwd, bool sampler, int *kc_out) {
   int forced = 0;
   if (const char *e = getenv(sampler ? "LFI_RPT_SAMPLE" : (bwd ? "LFI_RPT_BWD" : "LFI_RPT"))) forced = atoi(e);
   const int cand[4] = {8, 4, 2, 1};
-  int best = 0;
+  int best = 0, best_kc = KC16;
   for (int i = 0; i < 4; ++i) {
     const int rpt = cand[i], R = RG * rpt;
-    const int bytes = plan_smem(d, R, bwd, sampler).total * (int)sizeof(float);
-    if (bytes > kMaxSmem) continue;
-    if (forced == rpt) return rpt;
+    int kc = KC16;
+    if (plan_smem(d, R, bwd, sampler, kc).total * (int)sizeof(float) > kMaxSmem) {
+      kc = 8;
+      if (sampler || !kc_out || plan_smem(d, R, bwd, sampler, kc).total * (int)sizeof(float) > kMaxSmem) continue;
+    }
+    if (forced == rpt) { best = rpt; best_kc = kc; break; }
     const long ctas = (long)((B + R - 1) / R) * (sampler ? 1 : d.K);
-    best = rpt;
-    if (ctas >= (sampler ? 120 : 148)) return rpt;
+    best = rpt; best_kc = kc;
+    if (ctas >= (sampler ? 120 : 148)) break;
   }
+  if (kc_out) *kc_out = best_kc;
   return best;  // smallest tile that fits (0 = nothing fits)
 }
 
-template <int RPT> static int launch_fwd_t(const FwdArgs &a, cudaStream_t st) {
+int choose_rpt(const Dims &d, int B, bool bwd, bool sampler) { return choose_tile(d, B, bwd, sampler, nullptr); }
+
+template <int RPT, int KC> static int launch_fwd_t(const FwdArgs &a, cudaStream_t st) {
   constexpr int R = Tile<RPT>::R;
-  const int bytes = plan_smem(a.d, R, false, false).total * (int)sizeof(float);
-  LFI_CUDA(cudaFuncSetAttribute(core_fwd_wave<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  const int bytes = plan_smem(a.d, R, false, false, KC).total * (int)sizeof(float);
+  LFI_CUDA(cudaFuncSetAttribute(core_fwd_wave<RPT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   const int tiles = (a.B + R - 1) / R;
   const int nk = a.k_last - a.k_first + 1;
   const bool tcw = a.wtc.mode != 0 && a.k_first == 0 && !a.h0 && !a.c0;  // hybrid wavefronts: whole-sequence training forward only
@@ -341,7 +353,7 @@ template <int RPT> static int launch_fwd_t(const FwdArgs &a, cudaStream_t st) {
     const int i0 = max(0, wave - a.Tp + 1), i1 = min(nk - 1, wave);
     dim3 grid(tiles, i1 - i0 + 1);
     if (!tcw) {
-      core_fwd_wave<RPT><<<grid, NT, bytes, st>>>(a, wave + a.k_first, a.k_first + i0);
+      core_fwd_wave<RPT, KC><<<grid, NT, bytes, st>>>(a, wave + a.k_first, a.k_first + i0);
       continue;
     }
     FwdArgs aw = a;
@@ -358,7 +370,7 @@ template <int RPT> static int launch_fwd_t(const FwdArgs &a, cudaStream_t st) {
                        a.wtc.whh_lo ? (const uint16_t *)a.wtc.whh_lo + (size_t)kb0 * GH * H : nullptr, H, (long)GH * H);
       LFI_TRY(gemm_dispatch(a.wtc.mode, q, a.wtc.gws, a.wtc.gws_bytes, st));
     }
-    core_fwd_wave<RPT><<<grid, NT, bytes, st>>>(aw, wave, i0);
+    core_fwd_wave<RPT, KC><<<grid, NT, bytes, st>>>(aw, wave, i0);
   }
   LFI_LAUNCH_CHECK_N(a.Tp + nk - 1);
   return LFI_OK;
@@ -366,12 +378,17 @@ template <int RPT> static int launch_fwd_t(const FwdArgs &a, cudaStream_t st) {
 
 int launch_fwd(const FwdArgs &a, cudaStream_t st) {
   if (a.flags && !a.h0 && !a.c0 && pipe_supported(a.d, a.k_last - a.k_first + 1, false)) return launch_fwd_pipe(a, st);
-  const int rpt = choose_rpt(a.d, a.B, false, false);
-  switch (rpt) {
-    case 8: return launch_fwd_t<8>(a, st);
-    case 4: return launch_fwd_t<4>(a, st);
-    case 2: return launch_fwd_t<2>(a, st);
-    case 1: return launch_fwd_t<1>(a, st);
+  int kc = KC16;
+  const int rpt = choose_tile(a.d, a.B, false, false, &kc);
+  switch (rpt * 100 + kc) {
+    case 816: return launch_fwd_t<8, 16>(a, st);
+    case 416: return launch_fwd_t<4, 16>(a, st);
+    case 216: return launch_fwd_t<2, 16>(a, st);
+    case 116: return launch_fwd_t<1, 16>(a, st);
+    case 808: return launch_fwd_t<8, 8>(a, st);
+    case 408: return launch_fwd_t<4, 8>(a, st);
+    case 208: return launch_fwd_t<2, 8>(a, st);
+    case 108: return launch_fwd_t<1, 8>(a, st);
   }
   set_error("flow core: shape does not fit shared memory (H=%d G=%d C=%d)", a.d.H, a.d.G, a.d.C);
   return LFI_ERR_SHAPE;

@@ -16,9 +16,8 @@ constexpr int TX = 64;         // threads along output columns
 constexpr int RG = NT / TX;    // row groups
 constexpr int CPT = 6;         // columns per thread per chunk
 constexpr int WCH = TX * CPT;  // 384 columns per chunk
-constexpr int KC = 16;         // reduction rows per weight stage
+constexpr int KC16 = 16;       // reduction rows per weight stage (default ring)
 constexpr int NSTG = 4;        // weight stages in flight (ring): covers the L2 latency of the stream
-constexpr int WST_FLOATS = NSTG * KC * WCH;
 
 __device__ __forceinline__ void cp_async16(float *smem, const float *g) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -55,7 +54,9 @@ template <int RPT> struct Tile {
 // ranges (GRU backward) or a ring buffer (autoregressive window of the sampler).
 // Every thread of the CTA must call this (it contains __syncthreads); act must have been written before
 // the call (the first internal barrier orders it).  epi(r, j, v) is called once per owned output.
-template <int RPT, class Epi>
+// KC = reduction rows per ring stage: 16, or 8 (half the ring: 48 KB instead of 96 KB, which lets the wide shapes run
+// twice the rows per CTA; the bytes in flight, 3 stages x 12 KB, still cover the L2 latency of one SM's stream).
+template <int RPT, int KC = KC16, class Epi>
 __device__ __forceinline__ void tile_gemm(const float *act, const float *__restrict__ Wg, int ldw, int Kin, int N,
                                           float *wst, Epi epi, int split = 1 << 30, int shift_hi = 0, int shift_lo = 0) {
   constexpr int RS = Tile<RPT>::RS;
@@ -120,6 +121,48 @@ __device__ __forceinline__ void tile_gemm(const float *act, const float *__restr
   }
 }
 
+// Skinny product: out(r, j) = sum_i act[i][r] * Wg[i*ldw + j] for N <= 64 output columns and a long reduction (the
+// backward dz1 = dA_i W_ih[:, :Ci] with Kin = GH, LinearZeros with Kin = H).  tile_gemm would walk Kin / KC ring stages with a
+// CTA barrier each for a handful of columns; here the reduction is split over the warps instead: thread = (column j, slice
+// of Kin), weights straight from L2 (one coalesced row segment per warp and reduction index), activations as broadcast
+// float4 reads, partial sums combined through `scr` (>= (NT / NP) * R * NP floats; the weight ring is free at that point).
+// Every thread of the CTA must call this; act must be complete before the call (first barrier inside).
+template <int RPT, class Epi>
+__device__ __forceinline__ void skinny_gemm(const float *act, const float *__restrict__ Wg, int ldw, int Kin, int N, float *scr, Epi epi) {
+  constexpr int R = Tile<RPT>::R, RS = Tile<RPT>::RS;
+  const int tid = threadIdx.x;
+  const int NP = N <= 32 ? 32 : 64, NS = NT / NP;
+  const int j = tid % NP, sl = tid / NP;
+  const int per = (Kin + NS - 1) / NS, k0 = sl * per, k1 = min(Kin, k0 + per);
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  __syncthreads();
+  if (j < N) {
+#pragma unroll 4
+    for (int i = k0; i < k1; ++i) {
+      const float wv = __ldg(Wg + (size_t)i * ldw + j);
+      const float *ap = act + i * RS;
+#pragma unroll
+      for (int q = 0; q < R / 4; ++q) {
+        const float4 a4 = *reinterpret_cast<const float4 *>(ap + 4 * q);
+        acc[4 * q] = fmaf(a4.x, wv, acc[4 * q]); acc[4 * q + 1] = fmaf(a4.y, wv, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(a4.z, wv, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a4.w, wv, acc[4 * q + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) scr[(sl * R + r) * NP + j] = acc[r];
+  __syncthreads();
+  for (int e = tid; e < R * N; e += NT) {
+    const int r = e / N, c = e - r * N;
+    float v = 0.f;
+    for (int s2 = 0; s2 < NS; ++s2) v += scr[(s2 * R + r) * NP + c];
+    epi(r, c, v);
+  }
+  __syncthreads();  // scr (the weight ring) may be refilled
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -175,13 +218,13 @@ struct SmemPlan {
 // odd pitch => conflict-free column walks over row-major [R][pitch] arrays
 __host__ __device__ inline int odd(int n) { return n | 1; }
 
-__host__ __device__ inline SmemPlan plan_smem(const Dims &d, int R, bool bwd, bool sampler) {
+__host__ __device__ inline SmemPlan plan_smem(const Dims &d, int R, bool bwd, bool sampler, int kc = KC16) {
   const int RS = R + 4;
   const int Cm = d.Co > d.C ? d.Co : d.C;
   SmemPlan p;
   int o = 0;
   auto take = [&](int n) { int r = o; o += round_up(n, 4); return r; };
-  p.wst = take(WST_FLOATS);
+  p.wst = take(NSTG * kc * WCH);
   p.xs = take(Cm * RS);                        // act: ActNorm output y / inverse: coupling output / bwd: dlin
   p.zact = take(d.C * RS);                     // act: z1 (fwd) / dzf (bwd)
   p.zrow = take(R * odd(d.C));                 // row-major z (fwd) / zf -> dzf (bwd)
