@@ -53,10 +53,14 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
     }
     dldr[tid] = v;
   }
-  for (int e = tid; e < R * GH; e += NT) {
-    const int r = e / GH, j = e - r * GH;
-    S[r * pS + j] = (r < nrows) ? a.st.gates[(cell * B + row0 + r) * GH + j] : 0.f;
-  }
+  for (int r0 = 0; r0 < R; r0 += 4)  // four rows in flight per thread
+    for (int j = tid; j < GH; j += NT) {
+      float g[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g[i] = (r0 + i < nrows) ? __ldg(a.st.gates + (cell * B + row0 + r0 + i) * GH + j) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) S[(r0 + i) * pS + j] = g[i];
+    }
   for (int e = tid; e < R * H; e += NT) {
     const int r = e / H, m = e - r * H;
     float hv = 0.f, cv = 0.f, cnv = 0.f, an = 0.f;
@@ -165,13 +169,15 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
   }
   __syncthreads();
   // dA_i -> dG (time-parallel backward + db_ih), dA_h stash (dW_hh), db_hh, LSTM dc_prev
-  for (int e = tid; e < nrows * GH; e += NT) {
-    const int r = e / GH, j = e - r * GH;
-    const float vi = S[r * pS + j];
-    const float vh = (gru && j >= 2 * H) ? ahn[r * pH + j - 2 * H] : vi;
+  {
     const size_t gld = a.dg_ld ? (size_t)a.dg_ld : (size_t)d.K * GH;
-    a.dG[((size_t)t * B + row0 + r) * gld + (size_t)(k - a.dg_k0) * GH + j] = vi;
-    a.dAh[(cell * B + row0 + r) * GH + j] = vh;
+    for (int r = 0; r < nrows; ++r)
+      for (int j = tid; j < GH; j += NT) {
+        const float vi = S[r * pS + j];
+        const float vh = (gru && j >= 2 * H) ? ahn[r * pH + j - 2 * H] : vi;
+        a.dG[((size_t)t * B + row0 + r) * gld + (size_t)(k - a.dg_k0) * GH + j] = vi;
+        a.dAh[(cell * B + row0 + r) * GH + j] = vh;
+      }
   }
   for (int j = tid; j < GH; j += NT) {
     float s1 = 0.f;

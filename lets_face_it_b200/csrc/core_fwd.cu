@@ -29,28 +29,46 @@ __device__ __forceinline__ void coupling_net(const Dims &d, const StepWeights &w
   const int H = d.H, GH = d.GH, pS = odd(GH), pH = odd(H), pO = odd(d.Co > d.C ? d.Co : d.C);
   float *S = sm + sp.S, *ahn = sm + sp.ahn, *hp = sm + sp.hp, *cp = sm + sp.cp, *orow = sm + sp.orow;
 
-  // z1 part (and G init)
-  tile_gemm<RPT, KC>(sm + sp.zact, w.WzT, GH, d.Ci, GH, sm + sp.wst, [&](int r, int j, float v) {
-    if (Grow) S[r * pS + j] = v + (r < nrows ? Grow[(size_t)r * g_ld + j] : 0.f);
-    else S[r * pS + j] += v;
-  });
-  // h part
+  // time-parallel part of the gate pre-activations (and, hybrid wavefronts, the recurrent product that came from the batched
+  // tcgen05 GEMM; gh_rows == nullptr: zero state, t = 0): requested up front, four rows in flight per thread, so that their
+  // DRAM latency is paid once and overlaps the weight stream of the z1 product
   const bool gru = d.G == 3;
+  if (Grow) {
+    for (int r0 = 0; r0 < R; r0 += 4)
+      for (int j = tid; j < GH; j += NT) {
+        float g[4], hh[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool ok = r0 + i < nrows;
+          g[i] = ok ? __ldg(Grow + (size_t)(r0 + i) * g_ld + j) : 0.f;
+          hh[i] = (hh_pre && gh_rows && ok) ? __ldg(gh_rows + (size_t)(r0 + i) * GH + j) : 0.f;
+        }
+        const float bh = hh_pre ? w.b_hh[j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (hh_pre && gru && j >= 2 * H) { ahn[(r0 + i) * pH + (j - 2 * H)] = hh[i] + bh; S[(r0 + i) * pS + j] = g[i]; }
+          else S[(r0 + i) * pS + j] = g[i] + hh[i] + bh;
+        }
+      }
+  } else if (hh_pre) {
+    __syncthreads();
+    for (int r = 0; r < R; ++r)
+      for (int j = tid; j < GH; j += NT) {
+        float v = w.b_hh[j];
+        if (gh_rows && r < nrows) v += gh_rows[(size_t)r * GH + j];
+        if (gru && j >= 2 * H) ahn[r * pH + (j - 2 * H)] = v;
+        else S[r * pS + j] += v;
+      }
+  }
+  // z1 part
+  tile_gemm<RPT, KC>(sm + sp.zact, w.WzT, GH, d.Ci, GH, sm + sp.wst, [&](int r, int j, float v) { S[r * pS + j] += v; });
+  // h part
   if (!hh_pre) {
     tile_gemm<RPT, KC>(hp, w.WhhT, GH, H, GH, sm + sp.wst, [&](int r, int j, float v) {
       v += w.b_hh[j];
       if (gru && j >= 2 * H) ahn[r * pH + (j - 2 * H)] = v;
       else S[r * pS + j] += v;
     });
-  } else {  // hybrid wavefront: the product came from the batched tcgen05 GEMM (gh_rows == nullptr: zero state, t = 0)
-    __syncthreads();  // S was written by other threads in the z1 epilogue
-    for (int e = tid; e < R * GH; e += NT) {
-      const int r = e / GH, j = e - r * GH;
-      float v = w.b_hh[j];
-      if (gh_rows && r < nrows) v += gh_rows[(size_t)r * GH + j];
-      if (gru && j >= 2 * H) ahn[r * pH + (j - 2 * H)] = v;
-      else S[r * pS + j] += v;
-    }
   }
   __syncthreads();
   // gate math: lanes along rows
@@ -74,13 +92,17 @@ __device__ __forceinline__ void coupling_net(const Dims &d, const StepWeights &w
   __syncthreads();
   // stash (coalesced along columns)
   if (st_gates)
-    for (int e = tid; e < nrows * GH; e += NT) { const int r = e / GH, j = e - r * GH; st_gates[(size_t)r * GH + j] = S[r * pS + j]; }
+    for (int r = 0; r < nrows; ++r)
+      for (int j = tid; j < GH; j += NT) st_gates[(size_t)r * GH + j] = S[r * pS + j];
   if (st_ahn && gru)
-    for (int e = tid; e < nrows * H; e += NT) { const int r = e / H, j = e - r * H; st_ahn[(size_t)r * H + j] = ahn[r * pH + j]; }
+    for (int r = 0; r < nrows; ++r)
+      for (int j = tid; j < H; j += NT) st_ahn[(size_t)r * H + j] = ahn[r * pH + j];
   if (st_h)
-    for (int e = tid; e < nrows * H; e += NT) { const int r = e / H, j = e - r * H; st_h[(size_t)r * H + j] = hp[j * RS + r]; }
+    for (int r = 0; r < nrows; ++r)
+      for (int j = tid; j < H; j += NT) st_h[(size_t)r * H + j] = hp[j * RS + r];
   if (st_c && !gru)
-    for (int e = tid; e < nrows * H; e += NT) { const int r = e / H, j = e - r * H; st_c[(size_t)r * H + j] = cp[j * RS + r]; }
+    for (int r = 0; r < nrows; ++r)
+      for (int j = tid; j < H; j += NT) st_c[(size_t)r * H + j] = cp[j * RS + r];
   // LinearZeros (modules.py:93-95)
   if (d.Co <= 64)
     skinny_gemm<RPT>(hp, w.WfT, d.Cop, H, d.Co, sm + sp.wst, [&](int r, int j, float v) {

@@ -139,15 +139,19 @@ __device__ __forceinline__ void skinny_gemm(const float *act, const float *__res
   for (int r = 0; r < R; ++r) acc[r] = 0.f;
   __syncthreads();
   if (j < N) {
-#pragma unroll 4
-    for (int i = k0; i < k1; ++i) {
-      const float wv = __ldg(Wg + (size_t)i * ldw + j);
-      const float *ap = act + i * RS;
+    for (int i0 = k0; i0 < k1; i0 += 8) {  // eight weight rows requested before the first is used
+      float wv[8];
 #pragma unroll
-      for (int q = 0; q < R / 4; ++q) {
-        const float4 a4 = *reinterpret_cast<const float4 *>(ap + 4 * q);
-        acc[4 * q] = fmaf(a4.x, wv, acc[4 * q]); acc[4 * q + 1] = fmaf(a4.y, wv, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(a4.z, wv, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a4.w, wv, acc[4 * q + 3]);
+      for (int u = 0; u < 8; ++u) wv[u] = (i0 + u < k1) ? __ldg(Wg + (size_t)(i0 + u) * ldw + j) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float *ap = act + min(i0 + u, k1 - 1) * RS;
+#pragma unroll
+        for (int q = 0; q < R / 4; ++q) {
+          const float4 a4 = *reinterpret_cast<const float4 *>(ap + 4 * q);
+          acc[4 * q] = fmaf(a4.x, wv[u], acc[4 * q]); acc[4 * q + 1] = fmaf(a4.y, wv[u], acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(a4.z, wv[u], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a4.w, wv[u], acc[4 * q + 3]);
+        }
       }
     }
   }
