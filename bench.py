@@ -354,6 +354,22 @@ def run_ours(a):
     except Exception as e:  # secondary number only
         e2e_res = {"error": str(e)[:200]}
 
+    # ---- the same step captured once as a CUDA graph and replayed (single process) ---------------
+    graphed = None
+    if world == 1:
+        try:
+            gs = trainer.graphed(dbatch, warmup=1)
+            for _ in range(3):
+                gs.step()
+            sync()
+            ms_g = timed(lambda: gs.step(), a.steps)
+            graphed = {"value": frames_step * a.steps / (ms_g / 1e3), "unit": "frames/s", "ms_per_step": ms_g / a.steps,
+                       "note": "train.GraphedStep: every launch of Trainer.step (masks, forward, backward, clip, Adam; side streams "
+                               "included) replayed from one CUDA graph; learning rate and Adam bias corrections read from device memory"}
+            del gs
+        except Exception as e:  # secondary number only
+            graphed = {"error": str(e)[:300]}
+
     # ---- autoregressive sampling (second half of the metric): BASELINE.json configs[3] per-GPU share -------------------
     sample = None
     if not a.no_sample:
@@ -400,6 +416,8 @@ def run_ours(a):
         out["sample"] = sample
     if e2e_res is not None:
         out["e2e_resident"] = e2e_res
+    if graphed is not None:
+        out["graphed_step"] = graphed
 
     if rank == 0:
         # ---- roofline of the dominant contraction: cond_transform for all 16 steps, [B*56, 920] x [920, 8192] ---------

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LFI_ABI_VERSION 4
+#define LFI_ABI_VERSION 5
 #define LFI_NMOD 4 /* p1_face, p2_face, p1_speech, p2_speech — concat order of models.py:127-145 */
 
 typedef enum lfi_status {
@@ -210,6 +210,13 @@ int lfi_jerk(const float *x, int B, int T, int C, void *scratch8, float *out, vo
  * final_model.yaml:126,130): two launches, no host sync.  norm_scratch: 2 floats. */
 int lfi_clip_adam(float *theta, float *grad, float *m, float *v, size_t n, float lr, float beta1, float beta2,
                   float eps, float max_norm, float grad_scale, int step, float *norm_scratch, void *stream);
+
+/* The same update with the per-step scalars on the device: hyper[0] = learning rate, hyper[1] = 1 - beta1^step,
+ * hyper[2] = sqrt(1 - beta2^step) (computed by the caller in double, as torch.optim.Adam does).  Nothing in the launch
+ * arguments changes from step to step, so a whole training step can be captured in a CUDA graph and replayed
+ * (graph-capturable optimizer step; train.py: GraphedStep). */
+int lfi_clip_adam_dev(float *theta, float *grad, float *m, float *v, size_t n, const float *hyper, float beta1, float beta2,
+                      float eps, float max_norm, float grad_scale, float *norm_scratch, void *stream);
 
 /* generic batched GEMM used by the time-parallel phases (exposed for unit parity of the tcgen05 path)
  * C[b] = op(A[b]) op(B[b]) : transA: A stored [K,M]; transB: B stored [N,K]. epilogue flags below. */

@@ -591,7 +591,8 @@ int sumsq(float *out2, const float *g, size_t n, cudaStream_t st) {
 // (no weight decay, no amsgrad): the reference's configure_optimizers + gradient_clip_val.
 __global__ void clip_adam_kernel(float *theta, const float *grad, float *m, float *v, size_t n, float lr, float b1, float b2,
                                  float omb1, float omb2, float eps, float max_norm, float grad_scale, float bc1,
-                                 float bc2_sqrt, const float *sumsq_in) {
+                                 float bc2_sqrt, const float *sumsq_in, const float *hyper) {
+  if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2]; }  // captured launches: the per-step scalars live on the device
   const float norm = sqrtf(sumsq_in[0]) * grad_scale;
   float coef = 1.0f;
   if (max_norm > 0.f) coef = fminf(max_norm / (norm + 1e-6f), 1.0f);
@@ -616,14 +617,14 @@ __global__ void clip_adam_kernel(float *theta, const float *grad, float *m, floa
     upd(theta[e], grad[e], m[e], v[e]);
 }
 int clip_adam(float *theta, const float *grad, float *m, float *v, size_t n, float lr, float b1, float b2, float eps,
-              float max_norm, float grad_scale, int step, const float *sumsq_in, cudaStream_t st) {
+              float max_norm, float grad_scale, int step, const float *sumsq_in, cudaStream_t st, const float *hyper) {
   // scalar coefficients in double, as torch.optim.Adam computes them on the host
   const double b1d = (double)b1, b2d = (double)b2;
   const float bc1 = (float)(1.0 - pow(b1d, (double)step));
   const float bc2s = (float)sqrt(1.0 - pow(b2d, (double)step));
   clip_adam_kernel<<<blocks_for((n + 3) / 4, TB, 148 * 8), TB, 0, st>>>(theta, grad, m, v, n, lr, b1, b2, (float)(1.0 - b1d),
                                                                (float)(1.0 - b2d), eps, max_norm, grad_scale, bc1, bc2s,
-                                                               sumsq_in);
+                                                               sumsq_in, hyper);
   LFI_LAUNCH_CHECK();
   return LFI_OK;
 }

@@ -79,7 +79,7 @@ int lu_mask_grads(float *dl, float *du, float *dlog_s, const float *dL, const fl
 // clip_grad_norm_ + Adam over a flat buffer (lets_face_it_glow.py:61-72)
 int sumsq(float *out2, const float *g, size_t n, cudaStream_t st);
 int clip_adam(float *theta, const float *grad, float *m, float *v, size_t n, float lr, float b1, float b2, float eps,
-              float max_norm, float grad_scale, int step, const float *sumsq_in, cudaStream_t st);
+              float max_norm, float grad_scale, int step, const float *sumsq_in, cudaStream_t st, const float *hyper = nullptr);
 
 int fill(float *p, float v, size_t n, cudaStream_t st);
 

@@ -1170,6 +1170,14 @@ int lfi_clip_adam(float *theta, float *grad, float *m, float *v, size_t n, float
   return aux::clip_adam(theta, grad, m, v, n, lr, beta1, beta2, eps, max_norm, grad_scale, step, norm_scratch, st);
 }
 
+int lfi_clip_adam_dev(float *theta, float *grad, float *m, float *v, size_t n, const float *hyper, float beta1, float beta2, float eps,
+                      float max_norm, float grad_scale, float *norm_scratch, void *stream) {
+  LFI_REQUIRE(theta && grad && m && v && norm_scratch && hyper, LFI_ERR_ARG, "lfi_clip_adam_dev: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  LFI_TRY(aux::sumsq(norm_scratch, grad, n, st));
+  return aux::clip_adam(theta, grad, m, v, n, 0.f, beta1, beta2, eps, max_norm, grad_scale, 1, norm_scratch, st, hyper);
+}
+
 int lfi_gemm(int mode, int transA, int transB, int M, int N, int Kd, const float *A, int lda, long strideA, const float *Bm,
              int ldb, long strideB, float *Cm, int ldc, long strideC, const float *bias, long strideBias, const float *auxm,
              int ldaux, long strideAux, int batch, int epi, void *ws, size_t ws_bytes, void *stream) {

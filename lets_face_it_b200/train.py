@@ -104,6 +104,17 @@ class Trainer:
     def step(self, batch, masks=None, loss_scale=1.0):
         """One optimizer step on this rank's shard of sequences.  Returns the (device) loss of the shard (unscaled);
         `loss_scale` multiplies the loss the gradient is taken of (the -0.1 of the mismatched-NLL probe)."""
+        self.step_count += 1
+        return self._step_body(batch, masks, loss_scale, None)
+
+    def adam_scalars(self):
+        """(lr, 1 - beta1^step, sqrt(1 - beta2^step)) of the CURRENT step count, in double as torch.optim.Adam computes them."""
+        b1, b2 = float(self.betas[0]), float(self.betas[1])
+        return self.lr, 1.0 - b1 ** self.step_count, math.sqrt(1.0 - b2 ** self.step_count)
+
+    def _step_body(self, batch, masks, loss_scale, hyper):
+        """The launches of one step.  `hyper` (device, 3 floats = `adam_scalars()`): the per-step scalars are read on the device
+        (`lfi_clip_adam_dev`), so that the identical launch sequence can be captured once and replayed (GraphedStep)."""
         model = self.model
         eng = self.eng = model.engine()  # picks up a changed model.gemm_mode / a model moved to another device
         x0 = batch["p1_face"]
@@ -142,15 +153,81 @@ class Trainer:
             eng.train_backward(z, self._dnll[key], self.gflat)
             allreduce_flat_gradient(g, self.world, self.pg)  # sum; averaged by grad_scale below
         loss = nll.mean() - eng.logdet_const() / LN2  # before the update: the parameter-only log-det term belongs to THIS step's theta
-        self.step_count += 1
-        cabi.check(cabi.lib().lfi_clip_adam(eng.theta.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), eng.n_theta,
-                                            self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0 / self.world,
-                                            self.step_count, self.scratch.data_ptr(), cabi.stream_ptr()), "lfi_clip_adam")
+        L = cabi.lib()
+        if hyper is None:
+            cabi.check(L.lfi_clip_adam(eng.theta.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), eng.n_theta,
+                                       self.lr, self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0 / self.world,
+                                       self.step_count, self.scratch.data_ptr(), cabi.stream_ptr()), "lfi_clip_adam")
+        else:
+            cabi.check(L.lfi_clip_adam_dev(eng.theta.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), eng.n_theta,
+                                           hyper.data_ptr(), self.betas[0], self.betas[1], self.eps, self.max_norm, 1.0 / self.world,
+                                           self.scratch.data_ptr(), cabi.stream_ptr()), "lfi_clip_adam_dev")
         return loss
+
+    def graphed(self, batch, masks=None, warmup=3):
+        """A `GraphedStep` over batches of the shape of `batch`."""
+        return GraphedStep(self, batch, masks, warmup)
 
     def grad_norm(self):
         """Global gradient norm of the last step (after the all-reduce average, before clipping)."""
         return torch.sqrt(self.scratch[0]) / self.world
+
+
+class GraphedStep:
+    """One training step (frame-dropout masks, forward + NLL, backward, clip, Adam: every launch of `Trainer.step`, side streams
+    included) captured ONCE as a CUDA graph and replayed per step ("make the whole optimizer step
+    graph-capturable").  What makes the step capturable: no host synchronisation anywhere in it, every buffer owned by the
+    caller at a fixed address (grow-only workspace, flat theta / grad / Adam state), and the only scalars that change from
+    step to step - learning rate and Adam's bias corrections - read from device memory (`lfi_clip_adam_dev`).  The frame
+    dropout draws from torch's CUDA generator, which torch advances per replay.
+
+    `step(batch)` copies the batch into the captured input buffers, uploads the three scalars (pinned, stream ordered) and
+    replays; it returns the loss tensor of the captured step (overwritten by the next replay).  `warmup` eager steps run first
+    (they ARE optimizer steps: ActNorm data-dependent init, workspace growth and the library's per-shape caches happen there).
+    Single process only: with world_size > 1 the eager, stream-ordered `Trainer.step` is the path (its NCCL calls overlap the
+    backward through events that are handed to the library per call)."""
+
+    def __init__(self, trainer, batch, masks=None, warmup=3):
+        if trainer.world > 1:
+            raise NotImplementedError("GraphedStep: single-process only; use Trainer.step under torch.distributed")
+        tr = self.tr = trainer
+        dev = tr.eng.theta.device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedStep needs a CUDA device (no CPU path)")
+        self.static = {k: v.to(dev).float().contiguous().clone() for k, v in batch.items() if torch.is_tensor(v)}
+        self.masks = masks
+        self.hyper = torch.zeros(3, device=dev)
+        self._host = [torch.zeros(3).pin_memory() for _ in range(4)]
+        self._host_ev = [torch.cuda.Event() for _ in range(4)]
+        self._i = 0
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):
+                tr.step(self.static, masks)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = tr._step_body(self.static, masks, 1.0, self.hyper)
+
+    def step(self, batch=None):
+        tr = self.tr
+        if batch is not None:
+            for k, dst in self.static.items():
+                src = batch[k]
+                if src.data_ptr() != dst.data_ptr():
+                    dst.copy_(src, non_blocking=True)
+        tr.step_count += 1
+        j = self._i
+        self._i = (j + 1) % len(self._host)
+        self._host_ev[j].synchronize()  # the copy that last used this pinned slot has been executed
+        lr, bc1, bc2s = tr.adam_scalars()
+        self._host[j][0], self._host[j][1], self._host[j][2] = lr, bc1, bc2s
+        self.hyper.copy_(self._host[j], non_blocking=True)
+        self._host_ev[j].record()
+        self.graph.replay()
+        return self.loss
 
 
 class HostFeed:
