@@ -61,31 +61,40 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
 #pragma unroll
       for (int i = 0; i < 4; ++i) S[(r0 + i) * pS + j] = g[i];
     }
-  for (int e = tid; e < R * H; e += NT) {
-    const int r = e / H, m = e - r * H;
-    float hv = 0.f, cv = 0.f, cnv = 0.f, an = 0.f;
-    if (r < nrows) {
-      const size_t idx = (cell * B + row0 + r) * H + m;
-      if (t > 0) {
-        hv = a.st.h[idx - (size_t)B * H];
-        if (!gru) cv = a.st.c[idx - (size_t)B * H];
-      } else if (a.single >= 0) {  // module API: the state the cell started from is given
-        const size_t e1 = (size_t)(row0 + r) * H + m;
-        if (a.h_prev_ext) hv = a.h_prev_ext[e1];
-        if (!gru && a.c_prev_ext) cv = a.c_prev_ext[e1];
+  for (int r0 = 0; r0 < R; r0 += 4)  // four rows requested per thread before the first is used
+    for (int m = tid; m < H; m += NT) {
+      float hv[4], cv[4], cnv[4], an[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + i;
+        hv[i] = 0.f; cv[i] = 0.f; cnv[i] = 0.f; an[i] = 0.f;
+        if (r < nrows) {
+          const size_t idx = (cell * B + row0 + r) * H + m;
+          if (t > 0) {
+            hv[i] = a.st.h[idx - (size_t)B * H];
+            if (!gru) cv[i] = a.st.c[idx - (size_t)B * H];
+          } else if (a.single >= 0) {  // module API: the state the cell started from is given
+            const size_t e1 = (size_t)(row0 + r) * H + m;
+            if (a.h_prev_ext) hv[i] = a.h_prev_ext[e1];
+            if (!gru && a.c_prev_ext) cv[i] = a.c_prev_ext[e1];
+          }
+          if (gru) {
+            an[i] = a.st.ahn[idx];
+          } else {
+            cnv[i] = a.st.c[idx];
+            if (a.single >= 0) an[i] = a.dc_ext ? a.dc_ext[(size_t)(row0 + r) * H + m] : 0.f;
+            else an[i] = (t < Tp - 1) ? a.dc[idx + (size_t)B * H] : 0.f;  // dc flowing back from cell (k, t+1)
+          }
+        }
       }
-      if (gru) {
-        an = a.st.ahn[idx];
-      } else {
-        cnv = a.st.c[idx];
-        if (a.single >= 0) an = a.dc_ext ? a.dc_ext[(size_t)(row0 + r) * H + m] : 0.f;
-        else an = (t < Tp - 1) ? a.dc[idx + (size_t)B * H] : 0.f;  // dc flowing back from cell (k, t+1)
+      *reinterpret_cast<float4 *>(hp + m * RS + r0) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ahn[(r0 + i) * pH + m] = an[i];
+      if (!gru) {
+        *reinterpret_cast<float4 *>(cp + m * RS + r0) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+        *reinterpret_cast<float4 *>(cn + m * RS + r0) = make_float4(cnv[0], cnv[1], cnv[2], cnv[3]);
       }
     }
-    hp[m * RS + r] = hv;
-    ahn[r * pH + m] = an;
-    if (!gru) { cp[m * RS + r] = cv; cn[m * RS + r] = cnv; }
-  }
   __syncthreads();
 
   // ---- B. coupling backward (models.py:331-341) ---------------------------------------------------

@@ -34,18 +34,19 @@ __device__ __forceinline__ void coupling_net(const Dims &d, const StepWeights &w
   // DRAM latency is paid once and overlaps the weight stream of the z1 product
   const bool gru = d.G == 3;
   if (Grow) {
-    for (int r0 = 0; r0 < R; r0 += 4)
+    constexpr int NR = R >= 8 ? 8 : 4;  // rows in flight per thread
+    for (int r0 = 0; r0 < R; r0 += NR)
       for (int j = tid; j < GH; j += NT) {
-        float g[4], hh[4];
+        float g[NR], hh[NR];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NR; ++i) {
           const bool ok = r0 + i < nrows;
           g[i] = ok ? __ldg(Grow + (size_t)(r0 + i) * g_ld + j) : 0.f;
           hh[i] = (hh_pre && gh_rows && ok) ? __ldg(gh_rows + (size_t)(r0 + i) * GH + j) : 0.f;
         }
         const float bh = hh_pre ? w.b_hh[j] : 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NR; ++i) {
           if (hh_pre && gru && j >= 2 * H) { ahn[(r0 + i) * pH + (j - 2 * H)] = hh[i] + bh; S[(r0 + i) * pS + j] = g[i]; }
           else S[(r0 + i) * pS + j] = g[i] + hh[i] + bh;
         }
@@ -146,21 +147,21 @@ __global__ void __launch_bounds__(NT) core_fwd_wave(FwdArgs a, int wave, int kmi
     }
     xs[c * RS + r] = v;
   }
-  for (int e = tid; e < R * H; e += NT) {
-    const int r = e / H, m = e - r * H;
-    float hv = 0.f, cv = 0.f;
-    if (r < nrows) {
-      const int b = row0 + r;
-      if (t > 0) {
-        hv = a.st_h[((cell - 1) * B + b) * H + m];
-        if (d.G == 4) cv = a.st_c[((cell - 1) * B + b) * H + m];
-      } else {
-        if (a.h0) hv = a.h0[((size_t)k * B + b) * H + m];
-        if (d.G == 4 && a.c0) cv = a.c0[((size_t)k * B + b) * H + m];
+  {  // state the cell starts from (four rows requested per thread before the first is used)
+    const float *hsrc = t > 0 ? a.st_h + (cell - 1) * B * H : (a.h0 ? a.h0 + (size_t)k * B * H : nullptr);
+    const float *csrc = d.G != 4 ? nullptr : (t > 0 ? a.st_c + (cell - 1) * B * H : (a.c0 ? a.c0 + (size_t)k * B * H : nullptr));
+    for (int r0 = 0; r0 < R; r0 += 4)
+      for (int m = tid; m < H; m += NT) {
+        float hv[4], cv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool ok = r0 + i < nrows;
+          hv[i] = (ok && hsrc) ? hsrc[(size_t)(row0 + r0 + i) * H + m] : 0.f;
+          cv[i] = (ok && csrc) ? csrc[(size_t)(row0 + r0 + i) * H + m] : 0.f;
+        }
+        *reinterpret_cast<float4 *>(hp + m * RS + r0) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        if (d.G == 4) *reinterpret_cast<float4 *>(cp + m * RS + r0) = make_float4(cv[0], cv[1], cv[2], cv[3]);
       }
-    }
-    hp[m * RS + r] = hv;
-    if (d.G == 4) cp[m * RS + r] = cv;
   }
   // 2. invertible 1x1 conv (modules.py:186): z = y @ W
   tile_gemm<RPT, KC>(xs, w.Wfwd, d.Cp, C, C, sm + sp.wst, [&](int r, int j, float v) {
