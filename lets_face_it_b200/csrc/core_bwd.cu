@@ -185,7 +185,8 @@ __global__ void __launch_bounds__(NT) core_bwd_wave(BwdArgs a, int wave, int kmi
         const float vi = S[r * pS + j];
         const float vh = (gru && j >= 2 * H) ? ahn[r * pH + j - 2 * H] : vi;
         a.dG[((size_t)t * B + row0 + r) * gld + (size_t)(k - a.dg_k0) * GH + j] = vi;
-        a.dAh[(cell * B + row0 + r) * GH + j] = vh;
+        if (a.dAh) a.dAh[(cell * B + row0 + r) * GH + j] = vh;
+        if (a.pdAh_hi) put_plane(a.pdAh_hi, a.pdAh_lo, (cell * B + row0 + r) * GH + j, vh);  // hybrid wavefronts: operand planes
       }
   }
   for (int j = tid; j < GH; j += NT) {
@@ -276,8 +277,10 @@ template <int RPT, int KC> static int launch_bwd_t(const BwdArgs &a, cudaStream_
     if (kb1 >= kb0) {
       const int H = a.d.H, GH = a.d.GH, B = a.B, Tp = a.Tp;
       const size_t cell0 = (size_t)kb0 * Tp + (wave - kb0);     // (k, t) of the first cell; next cell: + (Tp - 1)
-      GemmArgs q = gemm_args(0, 0, B, H, GH, a.dAh + cell0 * B * GH, GH, nullptr, H, a.dh + cell0 * B * H, H, LFI_EPI_ACCUM);
+      GemmArgs q = gemm_args(0, 0, B, H, GH, a.dAh ? a.dAh + cell0 * B * GH : nullptr, GH, nullptr, H, a.dh + cell0 * B * H, H, LFI_EPI_ACCUM);
       q.batch = kb1 - kb0 + 1; q.sA = (long)(Tp - 1) * B * GH; q.sB = (long)GH * H; q.sC = (long)(Tp - 1) * B * H;
+      if (a.pdAh_hi)
+        q.pA = plane_ref((const uint16_t *)a.pdAh_hi + cell0 * B * GH, a.pdAh_lo ? (const uint16_t *)a.pdAh_lo + cell0 * B * GH : nullptr, GH, q.sA);
       q.pB = plane_ref((const uint16_t *)a.wtc.whh_hi + (size_t)kb0 * GH * H,
                        a.wtc.whh_lo ? (const uint16_t *)a.wtc.whh_lo + (size_t)kb0 * GH * H : nullptr, H, (long)GH * H);
       LFI_TRY(gemm_dispatch(a.wtc.mode, q, a.wtc.gws, a.wtc.gws_bytes, st));

@@ -180,6 +180,10 @@ __global__ void __launch_bounds__(NT) core_fwd_wave(FwdArgs a, int wave, int kmi
                     a.st_o ? a.st_o + rowbase * d.Co : nullptr, a.gh_pre != nullptr,
                     (a.gh_pre && t > 0) ? a.gh_pre + ((size_t)k * B + row0) * d.GH : nullptr);
 
+  if (a.ph_hi)  // hybrid wavefronts: the new state also as the operand plane(s) of the next wavefront's recurrent GEMM (and of dW_hh)
+    for (int r = 0; r < nrows; ++r)
+      for (int j = tid; j < H; j += NT) put_plane(a.ph_hi, a.ph_lo, (rowbase + r) * H + j, hp[j * RS + r]);
+
   // 4. coupling (models.py:331-341), log-det, NLL on the last step (modules.py:207-212, models.py:563-565)
   const float *orow = sm + sp.orow;
   const bool last = (k == a.k_last);
@@ -389,6 +393,8 @@ template <int RPT, int KC> static int launch_fwd_t(const FwdArgs &a, cudaStream_
       const size_t cellA = (size_t)kb0 * Tp + (wave - kb0 - 1);   // (k, t-1) of the first cell; next cell: + (Tp - 1)
       GemmArgs q = gemm_args(0, 1, B, GH, H, a.st_h + cellA * B * H, H, nullptr, H, gh + (size_t)kb0 * B * GH, GH, 0);
       q.batch = kb1 - kb0 + 1; q.sA = (long)(Tp - 1) * B * H; q.sB = (long)GH * H; q.sC = (long)B * GH;
+      if (a.ph_hi)  // the cells wrote their state as operand planes: no split pass in front of the product
+        q.pA = plane_ref((const uint16_t *)a.ph_hi + cellA * B * H, a.ph_lo ? (const uint16_t *)a.ph_lo + cellA * B * H : nullptr, H, q.sA);
       q.pB = plane_ref((const uint16_t *)a.wtc.whh_hi + (size_t)kb0 * GH * H,
                        a.wtc.whh_lo ? (const uint16_t *)a.wtc.whh_lo + (size_t)kb0 * GH * H : nullptr, H, (long)GH * H);
       LFI_TRY(gemm_dispatch(a.wtc.mode, q, a.wtc.gws, a.wtc.gws_bytes, st));

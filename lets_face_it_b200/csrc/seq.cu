@@ -233,6 +233,14 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
     two(w->dG_hi, w->dG_lo, M * K * d.GH); two(w->dAh_hi, w->dAh_lo, cells * d.GH);
     two(w->dO_hi, w->dO_lo, cells * d.Co); two(w->dzf_hi, w->dzf_lo, cells * d.C);
     two(w->dC_hi, w->dC_lo, M * K * d.D);
+  } else {
+    w->cact_hi = w->cact_lo = w->y_hi = w->y_lo = w->zf_hi = w->zf_lo = w->h_hi = w->h_lo = nullptr;
+    w->dG_hi = w->dG_lo = w->dAh_hi = w->dAh_lo = w->dO_hi = w->dO_lo = w->dzf_hi = w->dzf_lo = w->dC_hi = w->dC_lo = nullptr;
+    if (w->wave_tc) {  // hybrid wavefronts: the cells write the operands of the per-wavefront recurrent GEMMs (and of dW_hh, dWf) as planes
+      const bool lo = mode == LFI_GEMM_BF16X3;
+      w->h_hi = take_bf16(b, cells * d.H);      w->h_lo = lo ? take_bf16(b, cells * d.H) : nullptr;
+      w->dAh_hi = take_bf16(b, cells * d.GH);   w->dAh_lo = lo ? take_bf16(b, cells * d.GH) : nullptr;
+    }
   }
   w->bytes = round_up_sz(b.off, 256);
 }
@@ -548,6 +556,7 @@ int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params 
   if (w.cp) { a.py_hi = w.y_hi; a.py_lo = w.y_lo; a.pzf_hi = w.zf_hi; a.pzf_lo = w.zf_lo; a.ph_hi = w.h_hi; a.ph_lo = w.h_lo; }
   a.stash_tiled = w.st_tiled ? 1 : 0;
   a.g_tiled = w.st_tiled ? 1 : 0;
+  if (w.wave_tc) { a.ph_hi = w.h_hi; a.ph_lo = w.h_lo; }
   if (w.wave_tc) {  // recurrent weights as operand planes, once per call (they change with every optimizer step)
     LFI_TRY(split_to_planes(p->w_hh, d.GH, d.H, d.H, (long)d.GH * d.H, d.K, w.wt_hi, w.wt_lo, st));
     a.wtc.mode = gemm_mode; a.wtc.whh_hi = w.wt_hi; a.wtc.whh_lo = w.wt_lo; a.wtc.ghbuf = w.ghbuf; a.wtc.gws = gws; a.wtc.gws_bytes = gws_bytes;
@@ -591,6 +600,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
     a.g_b_ih = g->b_ih;
   }
   a.stash_tiled = w.st_tiled ? 1 : 0;
+  if (w.wave_tc) { a.pdAh_hi = w.dAh_hi; a.pdAh_lo = w.dAh_lo; a.dAh = nullptr; }  // the cells write dA_h as operand planes only
   if (w.wave_tc) {  // planes of W_hh were built by the forward call of this step
     a.wtc.mode = gemm_mode; a.wtc.whh_hi = w.wt_hi; a.wtc.whh_lo = w.wt_lo; a.wtc.ghbuf = w.ghbuf; a.wtc.gws = gws; a.wtc.gws_bytes = gws_bytes;
   }
@@ -619,7 +629,7 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
                    int ldc, long sC, PlaneRef pa = PlaneRef{nullptr, nullptr, 0, 0}, PlaneRef pb = PlaneRef{nullptr, nullptr, 0, 0}) -> int {
     GemmArgs q = gemm_args(1, 0, Mo, No, (int)red, A, lda, Bm, ldb, Cm, ldc, LFI_EPI_ACCUM);
     q.batch = K; q.sA = sA; q.sB = sB; q.sC = sC;
-    if (w.cp) { q.pA = pa; q.pB = pb; }
+    if (w.cp || w.wave_tc) { q.pA = pa; q.pB = pb; }  // (a plane reference with a null pointer means: split the fp32 operand)
     return gemm_dispatch(bmode, q, gws, gws_bytes, st);
   };
   const PlaneRef pdG = plane_ref(w.dG_hi, w.dG_lo, K * GH, GH), ph = plane_ref(w.h_hi, w.h_lo, H, (long)(M * H));
