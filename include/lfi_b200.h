@@ -89,6 +89,12 @@ long lfi_launch_count(void); /* kernels launched by this library since load (ben
  * rest of the call runs.  NULL clears the hook. */
 int lfi_set_grad_ready_event(void *event);
 
+/* Optional overlap hook of the training forward: `event` (cudaEvent_t) marks the derived cache `derived` (lfi_invconv_compose +
+ * lfi_derive, a chain of ~25 short launches per step) as rebuilt on ANOTHER stream.  While it is set, lfi_seq_train_fwd runs the
+ * conditioning encoders - which read their parameters directly - first and waits for the event only in front of the first
+ * consumer of the cache (the cond_transform GEMM), so the rebuild hides behind the encoder forward.  NULL clears the hook. */
+int lfi_set_derived_ready_event(void *event);
+
 /* ---- sizes ------------------------------------------------------------------------------- */
 int lfi_feature_dim(const lfi_shape *s);        /* F  = FeatureEncoder.dim (models.py:96-125)            */
 int lfi_feature_dim_folded(const lfi_shape *s); /* Fe = F with duplicated GRU halves folded (models.py:64) */

@@ -49,6 +49,7 @@ SYMBOLS = {
     "lfi_abi_version": (_I, []),
     "lfi_launch_count": (_L, []),
     "lfi_set_grad_ready_event": (_I, [_P]),
+    "lfi_set_derived_ready_event": (_I, [_P]),
     "lfi_expand_faces": (_I, [_P, _P, _P, _SZ, _I, _I, _I, _P, _P]),
     "lfi_feature_dim": (_I, [_SH]),
     "lfi_feature_dim_folded": (_I, [_SH]),

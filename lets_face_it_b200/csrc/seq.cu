@@ -497,6 +497,8 @@ static cudaEvent_t g_grad_ready_event = nullptr;
 extern "C" {
 
 int lfi_set_grad_ready_event(void *event) { g_grad_ready_event = (cudaEvent_t)event; return LFI_OK; }
+static cudaEvent_t g_derived_ready_event = nullptr;
+int lfi_set_derived_ready_event(void *event) { g_derived_ready_event = (cudaEvent_t)event; return LFI_OK; }
 
 int lfi_feature_dim(const lfi_shape *s) { Dims d; return make_dims(s, &d) == LFI_OK ? d.F : -1; }
 int lfi_feature_dim_folded(const lfi_shape *s) { Dims d; return make_dims(s, &d) == LFI_OK ? d.Fe : -1; }
@@ -541,6 +543,9 @@ int lfi_seq_train_fwd(const lfi_shape *s, const void *derived, const lfi_params 
   const float *WcF = (const float *)derived + L.WcF;
 
   LFI_TRY(build_cond(s, d, p, bt, d.start_ts, Tp, w.cond, w.enc, w.gh, true, false, true, gemm_mode, gws, gws_bytes, st));
+  // the encoders read their parameters directly; the derived cache (composed 1x1 weights, folded W_c, transposes) is first needed
+  // here - a caller that rebuilds it on another stream hands over the event to wait for (lfi_set_derived_ready_event)
+  if (g_derived_ready_event) LFI_CUDA(cudaStreamWaitEvent(st, g_derived_ready_event, 0));
   LFI_TRY(cond_to_gates(d, p, WcF, w.cond, M, w.Cact, w.G, gemm_mode, gws, gws_bytes, st, w.cp ? w.cact_hi : nullptr, w.cp ? w.cact_lo : nullptr,
                         w.st_tiled));
 
