@@ -280,6 +280,7 @@ __device__ __forceinline__ void chunk_to_rows(uint32_t taddr, float *stg, int la
 // pre-activations of those units, [64,128) u, [128,192) n (the B tile is gathered from the three gate blocks of W_hh).
 // Per 16-unit chunk: all global operands are requested first (they do not depend on the accumulator), then the
 // accumulator chunks are pulled out of TMEM, then gate math and stores.
+template <bool XF>  // XF: the input projections arrive in the accumulator (LFI_FUSE_GRU_FWD_X), columns [3UT,4UT) = n gate's input part
 __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t, uint32_t tbase, float *stg, int q, int half, int lane,
                                              uint64_t *tfull, uint32_t aph, int nsub) {
   const GruEpi &G = p.gru;
@@ -300,9 +301,13 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
       const int m = min(mrow0 + rr + 8 * i, p.M - 1);
       const int b = m % G.B, tp = m / G.B;
       const int tau = G.t0 + tp - G.hist + 1 + G.s;
-      mk[i] = G.mask ? G.mask[(size_t)m * G.hist + G.s] : 1.0f;
-      const float *xp = G.xp + ((size_t)b * G.T + tau) * 3 * E + e;
-      xr[i] = ld4_hint(xp, pol_keep); xu[i] = ld4_hint(xp + E, pol_keep); xn[i] = ld4_hint(xp + 2 * E, pol_keep);
+      if constexpr (!XF) {
+        mk[i] = G.mask ? G.mask[(size_t)m * G.hist + G.s] : 1.0f;
+        const float *xp = G.xp + ((size_t)b * G.T + tau) * 3 * E + e;
+        xr[i] = ld4_hint(xp, pol_keep); xu[i] = ld4_hint(xp + E, pol_keep); xn[i] = ld4_hint(xp + 2 * E, pol_keep);
+      } else {
+        mk[i] = 1.0f; xr[i] = xu[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // (already inside the r / u accumulators)
+      }
       hp[i] = ld4(G.hprev + (size_t)m * E + e);
     }
     const float4 bir = __ldg(reinterpret_cast<const float4 *>(G.b_ih + e)), biu = __ldg(reinterpret_cast<const float4 *>(G.b_ih + E + e)),
@@ -314,6 +319,12 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
     chunk_to_rows(tbase + sc * 16, stg, lane, rr, cg, ar);
     chunk_to_rows(tbase + UT + sc * 16, stg, lane, rr, cg, au);
     chunk_to_rows(tbase + 2 * UT + sc * 16, stg, lane, rr, cg, an);
+    if constexpr (XF) {
+      float ax[4][4];
+      chunk_to_rows(tbase + 3 * UT + sc * 16, stg, lane, rr, cg, ax);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xn[i] = make_float4(ax[i][0], ax[i][1], ax[i][2], ax[i][3]);
+    }
     if (u_base + 16 * sc + cg >= E) continue;
     const float bir_[4] = {bir.x, bir.y, bir.z, bir.w}, biu_[4] = {biu.x, biu.y, biu.z, biu.w}, bin_[4] = {bin.x, bin.y, bin.z, bin.w};
     const float bhr_[4] = {bhr.x, bhr.y, bhr.z, bhr.w}, bhu_[4] = {bhu.x, bhu.y, bhu.z, bhu.w}, bhn_[4] = {bhn.x, bhn.y, bhn.z, bhn.w};
@@ -436,7 +447,11 @@ __device__ __forceinline__ void gru_bwd_tile(const Params &p, const TileCoord &t
 template <int FUSE, int CL, int EW = kEpiWarps>
 __global__ void __launch_bounds__(threads_for(EW), 1)
 gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-               const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1) {
+               const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1,
+               const __grid_constant__ CUtensorMap mapXA0, const __grid_constant__ CUtensorMap mapXA1,
+               const __grid_constant__ CUtensorMap mapXB0, const __grid_constant__ CUtensorMap mapXB1) {
+  constexpr bool GRUF = FUSE == LFI_FUSE_GRU_FWD || FUSE == LFI_FUSE_GRU_FWD_X;   // fused GRU forward (with / without input part)
+  constexpr bool XF = FUSE == LFI_FUSE_GRU_FWD_X;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up: [stages][A planes | B planes] | epilogue staging | barriers | tmem address
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -500,7 +515,7 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
             } else {
               for (int j = 0; j < BM / 64; ++j) tma_load_3d(sa + pl * a_plane + j * (BK * 128), ma, &full[s], t.m0 + 64 * j, k0, t.b);
             }
-            if (FUSE == LFI_FUSE_GRU_FWD) {
+            if (GRUF) {
               // 64 hidden units x (r, u, n): three 64-row boxes of W_hh, 8-row swizzle atoms stay contiguous
               const int ut = p.bn / 3, u0 = (t.n0 / p.bn) * ut;  // (ut rows per gate box)
               for (int g = 0; g < 3; ++g) tma_load_3d(sb + pl * b_plane + g * (ut * 128), mb, &full[s], k0, g * p.gru.E + u0, t.b);
@@ -519,6 +534,21 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
             }
           }
           if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+        if constexpr (XF) {  // input part: k-blocks of [masked window inputs | W_ih], same stage geometry
+          const int nxb = (p.gru.xk + BK - 1) / BK;
+          const int ut = p.bn / 3, u0 = (t.n0 / p.bn) * ut;
+          for (int xb = 0; xb < nxb; ++xb) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], stage_bytes);
+            uint8_t *sa = smem + (size_t)s * stage_bytes;
+            uint8_t *sb = sa + p.nplanes * a_plane;
+            for (int pl = 0; pl < p.nplanes; ++pl) {
+              tma_load_3d(sa + pl * a_plane, pl ? &mapXA1 : &mapXA0, &full[s], xb * BK, t.m0, 0);
+              for (int g = 0; g < 3; ++g) tma_load_3d(sb + pl * b_plane + g * (ut * 128), pl ? &mapXB1 : &mapXB0, &full[s], xb * BK, g * p.gru.E + u0, 0);
+            }
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+          }
         }
       }
     }
@@ -560,6 +590,36 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
           else umma_commit(&empty[s]);
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
+        if constexpr (XF) {
+          // input part: r, u columns [0, 2 ut) accumulate on top of the recurrent product; the n gate's input part goes to its own
+          // column group [3 ut, 4 ut) (fresh accumulator per tile)
+          const int ut = p.bn / 3, nxb = (p.gru.xk + BK - 1) / BK;
+          const uint32_t idesc_ru = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * ut) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+          const uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ut >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+          uint32_t accn = 0;
+          for (int xb = 0; xb < nxb; ++xb) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+            const uint32_t sb = sa + p.nplanes * a_plane;
+            const int kleft = p.gru.xk - xb * BK;
+            const int nk = kleft >= BK ? BK / UK : (kleft + UK - 1) / UK;  // (the zero-filled tail of the k-block is skipped)
+            const int nprod = p.nplanes == 2 ? 3 : 1;
+            for (int pr = 0; pr < nprod; ++pr) {
+              const int pa = (pr == 2) ? 1 : 0, pb = (pr == 1) ? 1 : 0;
+              const uint64_t ad = make_sdesc(sa + pa * a_plane, 0, 1024);
+              const uint64_t bd = make_sdesc(sb + pb * b_plane, 0, 1024);
+              const uint64_t bdn = make_sdesc(sb + pb * b_plane + 2 * ut * 128, 0, 1024);
+              for (int k = 0; k < nk; ++k) {
+                umma_bf16(d_tmem, ad + (uint64_t)(k * ((UK * 2) >> 4)), bd + (uint64_t)(k * ((UK * 2) >> 4)), idesc_ru, 1u);
+                umma_bf16(d_tmem + 3 * ut, ad + (uint64_t)(k * ((UK * 2) >> 4)), bdn + (uint64_t)(k * ((UK * 2) >> 4)), idesc_n, accn);
+                accn = 1;
+              }
+            }
+            umma_commit(&empty[s]);
+            if (++s == p.stages) { s = 0; ph ^= 1; }
+          }
+        }
         if constexpr (CL == 2) umma_commit_2sm(&tfull[as]);  // accumulator complete (in both CTAs' TMEM)
         else umma_commit(&tfull[as]);
       }
@@ -592,7 +652,7 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
       bool waited = false;
       if constexpr (FUSE != LFI_FUSE_NONE) {
         const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
-        if constexpr (FUSE == LFI_FUSE_GRU_FWD) gru_fwd_tile(p, t, tb, stg, q, half, lane, &tfull[as], aph, EW / 4);
+        if constexpr (GRUF) gru_fwd_tile<XF>(p, t, tb, stg, q, half, lane, &tfull[as], aph, EW / 4);
         else gru_bwd_tile(p, t, tb, stg, q, half, lane, &tfull[as], aph, EW / 4);
         waited = true;
       }
@@ -833,11 +893,16 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
   p.bn = choose_bn(g.N);
   p.fuse = g.fuse; p.gru = g.gru;
-  if (g.fuse == LFI_FUSE_GRU_FWD) {
+  const bool gruf = g.fuse == LFI_FUSE_GRU_FWD || g.fuse == LFI_FUSE_GRU_FWD_X;
+  if (gruf) {
     LFI_REQUIRE(g.gru.E % 64 == 0 && g.N == 3 * g.gru.E && !B.mn && g.batch == 1, LFI_ERR_SHAPE, "gemm_tc: fused GRU forward needs E %% 64 == 0");
     // 64 hidden units per tile, or 32 (LFI_GRU_TILE32=1): twice the tiles, half the epilogue per tile, a finer last wave
     static const bool tile32 = env_flag("LFI_GRU_TILE32", false);
-    p.bn = tile32 ? 96 : 192;
+    p.bn = (tile32 && g.fuse == LFI_FUSE_GRU_FWD) ? 96 : 192;
+    if (g.fuse == LFI_FUSE_GRU_FWD_X)
+      LFI_REQUIRE(g.gru.xa_hi && g.gru.xb_hi && (nplanes == 1 || (g.gru.xa_lo && g.gru.xb_lo)) && g.gru.xk >= 8 && g.gru.xk % 8 == 0 &&
+                      g.gru.xa_ld % 8 == 0 && g.gru.xb_ld % 8 == 0,
+                  LFI_ERR_ARG, "gemm_tc: fused GRU forward with input part needs the input / W_ih operand planes (pitch %% 8 == 0)");
     const float *cd = g.gru.cond;
     p.cond_vec = cd && (((uintptr_t)cd & 15) == 0) && g.gru.cond_ld % 4 == 0;
   } else if (g.fuse == LFI_FUSE_GRU_BWD) {
@@ -874,7 +939,7 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   const int CL = pair ? 2 : 1;
   p.tiles_m = (g.M + BM - 1) / BM; p.tiles_n = (g.N + p.bn - 1) / p.bn;
   const int stage_bytes = nplanes * (BM * BK * 2 + (p.bn / CL) * BK * 2);  // per CTA
-  const int ew = g.fuse == LFI_FUSE_GRU_FWD ? kGruEpiWarps : kEpiWarps;
+  const int ew = gruf ? kGruEpiWarps : kEpiWarps;
   const int fixed = epi_bytes_for(ew) + (2 * kMaxStages + 4) * 8 + 16 + 1024;
   p.stages = (kSmemLimit - fixed) / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -915,7 +980,7 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   if (g.pOut.hi) p.vec = p.vec && al16(g.pOut.hi) && (!g.pOut.lo || al16(g.pOut.lo)) && g.pOut.ld % 4 == 0 && g.pOut.stride % 4 == 0;
 
   CUtensorMap mA0, mA1, mB0, mB1;
-  const int a_box = A.mn ? BK : BM, b_box = B.mn ? BK : (g.fuse == LFI_FUSE_GRU_FWD ? p.bn / 3 : (pair ? p.bn / 2 : p.bn));
+  const int a_box = A.mn ? BK : BM, b_box = B.mn ? BK : (gruf ? p.bn / 3 : (pair ? p.bn / 2 : p.bn));
   LFI_TRY(make_map(&mA0, A.hi, A.rows, A.cols, A.ldp, A.stride, g.batch, a_box));
   LFI_TRY(make_map(&mB0, B.hi, B.rows, B.cols, B.ldp, B.stride, g.batch, b_box));
   if (nplanes == 2) {
@@ -924,12 +989,25 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   } else {
     mA1 = mA0; mB1 = mB0;
   }
+  CUtensorMap mXA0 = mA0, mXA1 = mA1, mXB0 = mB0, mXB1 = mB1;  // (placeholders unless the input part is fused)
+  if (g.fuse == LFI_FUSE_GRU_FWD_X) {
+    const GruEpi &G = g.gru;
+    LFI_TRY(make_map(&mXA0, (const __nv_bfloat16 *)G.xa_hi, g.M, G.xk, G.xa_ld, 0, 1, BM));
+    LFI_TRY(make_map(&mXB0, (const __nv_bfloat16 *)G.xb_hi, g.N, G.xk, G.xb_ld, 0, 1, p.bn / 3));
+    if (nplanes == 2) {
+      LFI_TRY(make_map(&mXA1, (const __nv_bfloat16 *)G.xa_lo, g.M, G.xk, G.xa_ld, 0, 1, BM));
+      LFI_TRY(make_map(&mXB1, (const __nv_bfloat16 *)G.xb_lo, g.N, G.xk, G.xb_ld, 0, 1, p.bn / 3));
+    } else {
+      mXA1 = mXA0; mXB1 = mXB0;
+    }
+  }
   const int smem = p.stages * stage_bytes + fixed;
   static bool attr_set = false;
   if (!attr_set) {
     LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_NONE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_NONE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_GRU_FWD, 1, kGruEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_GRU_FWD_X, 1, kGruEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     LFI_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<LFI_FUSE_GRU_BWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
@@ -937,8 +1015,9 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
   const int grid = (int)(ntiles < g_sms ? ntiles : g_sms);
   // request > half of the SM's shared memory so that two CTAs (each wanting all 512 TMEM columns) never share an SM
   const int smem_req = smem < 120 * 1024 ? 120 * 1024 : smem;
-  if (g.fuse == LFI_FUSE_GRU_FWD) gemm_tc_kernel<LFI_FUSE_GRU_FWD, 1, kGruEpiWarps><<<grid, threads_for(kGruEpiWarps), smem_req, st>>>(p, mA0, mA1, mB0, mB1);
-  else if (g.fuse == LFI_FUSE_GRU_BWD) gemm_tc_kernel<LFI_FUSE_GRU_BWD, 1><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
+  if (g.fuse == LFI_FUSE_GRU_FWD) gemm_tc_kernel<LFI_FUSE_GRU_FWD, 1, kGruEpiWarps><<<grid, threads_for(kGruEpiWarps), smem_req, st>>>(p, mA0, mA1, mB0, mB1, mXA0, mXA1, mXB0, mXB1);
+  else if (g.fuse == LFI_FUSE_GRU_FWD_X) gemm_tc_kernel<LFI_FUSE_GRU_FWD_X, 1, kGruEpiWarps><<<grid, threads_for(kGruEpiWarps), smem_req, st>>>(p, mA0, mA1, mB0, mB1, mXA0, mXA1, mXB0, mXB1);
+  else if (g.fuse == LFI_FUSE_GRU_BWD) gemm_tc_kernel<LFI_FUSE_GRU_BWD, 1><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1, mXA0, mXA1, mXB0, mXB1);
   else if (pair) {
     // CTA pairs: one 256-row cta_group::2 tile per cluster
     cudaLaunchConfig_t cfg;
@@ -950,8 +1029,8 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    LFI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<LFI_FUSE_NONE, 2>, p, mA0, mA1, mB0, mB1));
-  } else gemm_tc_kernel<LFI_FUSE_NONE, 1><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1);
+    LFI_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<LFI_FUSE_NONE, 2>, p, mA0, mA1, mB0, mB1, mXA0, mXA1, mXB0, mXB1));
+  } else gemm_tc_kernel<LFI_FUSE_NONE, 1><<<grid, kThreads, smem_req, st>>>(p, mA0, mA1, mB0, mB1, mXA0, mXA1, mXB0, mXB1);
   LFI_LAUNCH_CHECK();
   return LFI_OK;
 }

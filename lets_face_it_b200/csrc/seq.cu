@@ -89,6 +89,8 @@ struct EncWs {
   float *dah32, *dan32;   // fp32 mode: [hist][M][3E], [hist][M][E]
   void *dah_hi, *dah_lo, *dan_hi, *dan_lo;  // planes, same shapes
   void *xg_hi, *xg_lo;    // masked window inputs [hist][M][round_up(dim, 8)]
+  void *wih_hi, *wih_lo;  // W_ih       [3E][round_up(dim, 8)]  (input part of the fused forward step, LFI_FUSE_GRU_FWD_X)
+  bool xfuse;             // the forward steps s >= 1 take their input projection inside the step GEMM (training, per-step path)
   float *xg32;            // the same in fp32 [hist][M][dim] (split source / fp32-mode operand)
   float *dhe;             // [M][E] running d h of the window recurrence
   // persistent window-GRU kernels (enc_persist.cu): xp is time-major and row-interleaved, the stash (hs, gates, ahn, dhe) is
@@ -182,6 +184,10 @@ static void plan_train(const lfi_shape *s, const Dims &d, int B, int T, int mode
       e.dah_hi = take_bf16(b, h * M * 3 * E);       e.dah_lo = lo ? take_bf16(b, h * M * 3 * E) : nullptr;
       e.dan_hi = take_bf16(b, h * M * E);           e.dan_lo = lo ? take_bf16(b, h * M * E) : nullptr;
       e.xg_hi = take_bf16(b, h * M * dimp);         e.xg_lo = lo ? take_bf16(b, h * M * dimp) : nullptr;
+      e.wih_hi = take_bf16(b, 3 * E * dimp);        e.wih_lo = lo ? take_bf16(b, 3 * E * dimp) : nullptr;
+      // input projection inside the fused step GEMM: the masked window inputs are gathered as operand planes in the forward pass
+      // (the backward pass needs them anyway for dW_ih) and W_ih joins the B operand; step 0 (no state yet) keeps the xp rows
+      e.xfuse = !e.persist && E % 64 == 0 && env_flag("LFI_FUSED_GRU_FWD", true) && env_flag("LFI_ENC_XFUSE", true);
     } else {
       e.dah32 = b.take<float>(h * M * 3 * E);
       e.dan32 = b.take<float>(h * M * E);
@@ -316,6 +322,11 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
     EncWs &ew = enc[m];
     if (ew.planes && project)  // W_hh planes: once per call (weights change every optimizer step)
       LFI_TRY(split_to_planes(p->enc_w_hh[m], 3 * E, E, E, 0, 1, ew.whh_hi, lo ? ew.whh_lo : nullptr, st));
+    if (ew.planes && stash && ew.xfuse && ew.xg_hi) {
+      const int dimp = round_up(dim, 8);
+      LFI_TRY(aux::gather_windows_planes(ew.xg_hi, lo ? ew.xg_lo : nullptr, dimp, bt->x[m], bt->mask[m], B, T, dim, hist, 1, t0, Tp, st));
+      LFI_TRY(split_to_planes(p->enc_w_ih[m], 3 * E, dim, dim, 0, 1, ew.wih_hi, lo ? ew.wih_lo : nullptr, st));
+    }
     mods[nmods++] = m;
     all_fused = all_fused && ew.planes && (ew.persist || (E % 64 == 0 && env_flag("LFI_FUSED_GRU_FWD", true)));
   }
@@ -371,6 +382,12 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
         gg.pB = plane_ref(ew.whh_hi, ew.whh_lo, E);
         gg.fuse = LFI_FUSE_GRU_FWD;
         GruEpi &q = gg.gru;
+        if (stash && ew.xfuse && ew.xg_hi) {
+          const int dimp = round_up(s->dim[m], 8);
+          gg.fuse = LFI_FUSE_GRU_FWD_X;
+          q.xa_hi = (uint16_t *)ew.xg_hi + (size_t)sidx * M * dimp; q.xa_lo = lo ? (uint16_t *)ew.xg_lo + (size_t)sidx * M * dimp : nullptr;
+          q.xb_hi = ew.wih_hi; q.xb_lo = lo ? ew.wih_lo : nullptr; q.xa_ld = dimp; q.xb_ld = dimp; q.xk = dimp;
+        }
         q.E = E; q.s = sidx; q.hist = hist; q.B = B; q.T = T; q.t0 = t0; q.gates16 = a.gates16;
         q.xp = a.xp; q.b_ih = a.b_ih; q.b_hh = a.b_hh; q.mask = a.mask; q.hprev = a.hprev;
         q.h = a.h; q.gates = a.gates; q.ahn = a.ahn; q.cond = a.cond; q.cond_ld = a.cond_ld; q.h_hi = a.h_hi; q.h_lo = a.h_lo;
@@ -723,7 +740,9 @@ int lfi_seq_train_bwd(const lfi_shape *s, const void *derived, const lfi_params 
     EncWs &ew = w.enc[m];
     const bool lo = gemm_mode == LFI_GEMM_BF16X3;
     const int dimp = round_up(dim, 8);
-    if (ew.planes)  // masked window inputs straight into the operand planes of the dW_ih GEMMs
+    if (ew.planes && ew.xfuse) {
+      // (gathered by the forward pass of this step, which fed them to its fused step GEMMs)
+    } else if (ew.planes)  // masked window inputs straight into the operand planes of the dW_ih GEMMs
       LFI_TRY(aux::gather_windows_planes(ew.xg_hi, lo ? ew.xg_lo : nullptr, dimp, bt->x[m], bt->mask[m], B, T, dim, hist, 1, d.start_ts, Tp, st));
     else
       LFI_TRY(aux::gather_windows(ew.xg32, dim, 1, bt->x[m], bt->mask[m], B, T, dim, hist, 1, d.start_ts, Tp, st));
