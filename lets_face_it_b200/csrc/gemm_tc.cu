@@ -308,7 +308,7 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
       } else {
         mk[i] = 1.0f; xr[i] = xu[i] = make_float4(0.f, 0.f, 0.f, 0.f);  // (already inside the r / u accumulators)
       }
-      hp[i] = ld4(G.hprev + (size_t)m * E + e);
+      hp[i] = G.hprev ? ld4(G.hprev + (size_t)m * E + e) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float4 bir = __ldg(reinterpret_cast<const float4 *>(G.b_ih + e)), biu = __ldg(reinterpret_cast<const float4 *>(G.b_ih + E + e)),
                  bin = __ldg(reinterpret_cast<const float4 *>(G.b_ih + 2 * E + e));
@@ -324,6 +324,12 @@ __device__ __forceinline__ void gru_fwd_tile(const Params &p, const TileCoord &t
       chunk_to_rows(tbase + 3 * UT + sc * 16, stg, lane, rr, cg, ax);
 #pragma unroll
       for (int i = 0; i < 4; ++i) xn[i] = make_float4(ax[i][0], ax[i][1], ax[i][2], ax[i][3]);
+      if (G.x_only) {  // no recurrent product was issued: the h-side n columns of the accumulator were never written
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) an[i][c] = 0.f;
+      }
     }
     if (u_base + 16 * sc + cg >= E) continue;
     const float bir_[4] = {bir.x, bir.y, bir.z, bir.w}, biu_[4] = {biu.x, biu.y, biu.z, biu.w}, bin_[4] = {bin.x, bin.y, bin.z, bin.w};
@@ -494,7 +500,8 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
       int s = 0; uint32_t ph = 0;
       for (int tile = tile0; tile < ntiles; tile += tstride) {
         const TileCoord t = tile_coord(p, tile, nkb, CL, rank);
-        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+        const int kb_end = (XF && p.gru.x_only) ? t.kb0 : t.kb1;
+        for (int kb = t.kb0; kb < kb_end; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           if (CL == 1 || rank == 0) mbar_expect_tx(&full[s], CL * stage_bytes);  // pair: both CTAs' loads land on the leader's barrier
           const uint32_t fbar = CL > 1 ? mapa_u32(smem_u32(&full[s]), 0) : 0;
@@ -568,7 +575,8 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 256;
         uint32_t acc = 0;
-        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+        const int kb_end = (XF && p.gru.x_only) ? t.kb0 : t.kb1;
+        for (int kb = t.kb0; kb < kb_end; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
@@ -611,7 +619,8 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
               const uint64_t bd = make_sdesc(sb + pb * b_plane, 0, 1024);
               const uint64_t bdn = make_sdesc(sb + pb * b_plane + 2 * ut * 128, 0, 1024);
               for (int k = 0; k < nk; ++k) {
-                umma_bf16(d_tmem, ad + (uint64_t)(k * ((UK * 2) >> 4)), bd + (uint64_t)(k * ((UK * 2) >> 4)), idesc_ru, 1u);
+                umma_bf16(d_tmem, ad + (uint64_t)(k * ((UK * 2) >> 4)), bd + (uint64_t)(k * ((UK * 2) >> 4)), idesc_ru, acc);
+                acc = 1;
                 umma_bf16(d_tmem + 3 * ut, ad + (uint64_t)(k * ((UK * 2) >> 4)), bdn + (uint64_t)(k * ((UK * 2) >> 4)), idesc_n, accn);
                 accn = 1;
               }

@@ -158,6 +158,7 @@ struct GruEpi {
   void *h_hi, *h_lo;
   // LFI_FUSE_GRU_FWD_X: masked window inputs of this step [M, xk] and W_ih [3E, xk] as operand planes (pitches in elements)
   const void *xa_hi, *xa_lo, *xb_hi, *xb_lo; int xa_ld, xb_ld, xk;
+  int x_only;  // window step 0: zero state, no recurrent product - the launch consists of the input part alone (hprev == nullptr)
   // backward: the GEMM of step s yields dh_{s-1}; the epilogue runs the gate backward of step s-1
   const float *bgates, *bahn, *bhprev;   // stash of step s-1 (bhprev = h_{s-2}, nullptr when s-1 == 0)
   float *dh;                             // [M][E] in: direct part dh_s * u_s, out: dh_{s-1} * u_{s-1}

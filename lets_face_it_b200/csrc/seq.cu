@@ -315,7 +315,7 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
       GemmArgs g = gemm_args(0, 1, B * T, 3 * E, dim, enc[m].xT, dim, p->enc_w_ih[m], dim, enc[m].xp, 3 * E);
       g.c_tiled32 = 1;
       LFI_TRY(gemm_dispatch(mode, g, gws, gws_bytes, st));
-    } else if (project) {
+    } else if (project && !(stash && enc[m].planes && enc[m].xfuse && enc[m].xg_hi)) {  // (fused into the step GEMMs otherwise)
       GemmArgs g = gemm_args(0, 1, B * T, 3 * E, dim, bt->x[m], dim, p->enc_w_ih[m], dim, enc[m].xp, 3 * E);
       LFI_TRY(gemm_dispatch(mode, g, gws, gws_bytes, st));
     }
@@ -356,7 +356,8 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
       const int cur = stash ? sidx : (sidx & 1), prv = stash ? sidx - 1 : ((sidx - 1) & 1);
       hcur = ew.hs + (size_t)cur * M * E;
       if (sidx) hprev = ew.hs + (size_t)prv * M * E;
-      const bool fused = sidx && ew.planes && E % 64 == 0 && env_flag("LFI_FUSED_GRU_FWD", true);
+      const bool xf = stash && ew.planes && ew.xfuse && ew.xg_hi;  // input projection inside the step GEMM: also step 0 (input part alone)
+      const bool fused = (sidx || xf) && ew.planes && E % 64 == 0 && env_flag("LFI_FUSED_GRU_FWD", true);
       if (sidx && !fused) {
         GemmArgs gg = gemm_args(0, 1, (int)M, 3 * E, E, hprev, E, p->enc_w_hh[m], E, gh, 3 * E);
         if (ew.planes) {
@@ -378,7 +379,8 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
       if (fused) {
         // recurrent product and gate math in one launch: the [M, 3E] pre-activations stay in TMEM
         GemmArgs gg = gemm_args(0, 1, (int)M, 3 * E, E, nullptr, E, nullptr, E, nullptr, 3 * E);
-        gg.pA = plane_ref((uint16_t *)ew.hp_hi + (size_t)prv * M * E, lo ? (uint16_t *)ew.hp_lo + (size_t)prv * M * E : nullptr, E);
+        const size_t pslot = sidx ? (size_t)prv : 0;  // (step 0 reads no state: the plane reference only shapes the tensor map)
+        gg.pA = plane_ref((uint16_t *)ew.hp_hi + pslot * M * E, lo ? (uint16_t *)ew.hp_lo + pslot * M * E : nullptr, E);
         gg.pB = plane_ref(ew.whh_hi, ew.whh_lo, E);
         gg.fuse = LFI_FUSE_GRU_FWD;
         GruEpi &q = gg.gru;
@@ -387,6 +389,7 @@ static int build_cond(const lfi_shape *s, const Dims &d, const lfi_params *p, co
           gg.fuse = LFI_FUSE_GRU_FWD_X;
           q.xa_hi = (uint16_t *)ew.xg_hi + (size_t)sidx * M * dimp; q.xa_lo = lo ? (uint16_t *)ew.xg_lo + (size_t)sidx * M * dimp : nullptr;
           q.xb_hi = ew.wih_hi; q.xb_lo = lo ? ew.wih_lo : nullptr; q.xa_ld = dimp; q.xb_ld = dimp; q.xk = dimp;
+          q.x_only = sidx == 0 ? 1 : 0;
         }
         q.E = E; q.s = sidx; q.hist = hist; q.B = B; q.T = T; q.t0 = t0; q.gates16 = a.gates16;
         q.xp = a.xp; q.b_ih = a.b_ih; q.b_hh = a.b_hh; q.mask = a.mask; q.hprev = a.hprev;
