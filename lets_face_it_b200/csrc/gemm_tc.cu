@@ -907,7 +907,7 @@ static int launch_core(const Operand &A, const Operand &B, const GemmArgs &g, in
     LFI_REQUIRE(g.gru.E % 64 == 0 && g.N == 3 * g.gru.E && !B.mn && g.batch == 1, LFI_ERR_SHAPE, "gemm_tc: fused GRU forward needs E %% 64 == 0");
     // 64 hidden units per tile, or 32 (LFI_GRU_TILE32=1): twice the tiles, half the epilogue per tile, a finer last wave
     static const bool tile32 = env_flag("LFI_GRU_TILE32", false);
-    p.bn = (tile32 && g.fuse == LFI_FUSE_GRU_FWD) ? 96 : 192;
+    p.bn = tile32 ? 96 : 192;
     if (g.fuse == LFI_FUSE_GRU_FWD_X)
       LFI_REQUIRE(g.gru.xa_hi && g.gru.xb_hi && (nplanes == 1 || (g.gru.xa_lo && g.gru.xb_lo)) && g.gru.xk >= 8 && g.gru.xk % 8 == 0 &&
                       g.gru.xa_ld % 8 == 0 && g.gru.xb_ld % 8 == 0,
