@@ -54,6 +54,12 @@ __host__ __device__ inline PipePlan plan_pipe(const Dims &d) {
   return p;
 }
 
+// e / c for a divisor that is constant over the launch (the channel count, 56): one multiply-high instead of the ~20-instruction
+// integer division, inside loops that sit on the per-frame critical path.  magic = ceil(2^32 / c); exact for e * (magic * c - 2^32) < 2^32,
+// i.e. for every e below 2^32 / c.
+__device__ __forceinline__ unsigned div_magic(int c) { return (unsigned)((0x100000000ull + (unsigned)c - 1) / (unsigned)c); }
+__device__ __forceinline__ int fast_div(int e, unsigned magic) { return (int)__umulhi((unsigned)e, magic); }
+
 // fp32 -> split-bf16 operand planes (gemm_tc.cu): hi = bf16(v), lo = bf16(v - hi)
 __device__ __forceinline__ void put_plane(void *hi, void *lo, size_t idx, float v) {
   const __nv_bfloat16 h = __float2bfloat16_rn(v);

@@ -82,6 +82,7 @@ core_bwd_pipe_tc(const BwdArgs a, const int P, const int ntiles, int *progress) 
   const int c = (int)cluster.block_rank();
   const int k = blockIdx.y, K = d.K, p = blockIdx.z;
   const int C = d.C, Ci = d.Ci, Cz = d.Cz, Co = d.Co, H = d.H, GH = d.GH, B = a.B, Tp = a.Tp, Cp = d.Cp, Cip = d.Cip;
+  const unsigned magC = div_magic(C), magCi = div_magic(Ci);
   const PlanBT pl = plan_bt(d);
   const int pC = pl.pC;
   float *wT = (float *)(smb + pl.wT), *ans = (float *)(smb + pl.vec), *e3 = ans + C;
@@ -497,7 +498,7 @@ core_bwd_pipe_tc(const BwdArgs a, const int P, const int ntiles, int *progress) 
 
       // ---- 6. finish d(1x1 conv output), dy = dzf @ W^T, ActNorm backward (modules.py:45-66) ------------------------------
       for (int e = tid; e < PRH * Ci; e += PNT) {
-        const int r = e / Ci, i = e - r * Ci;
+        const int r = fast_div(e, magCi), i = e - r * Ci;
         dzf[r * pC + i] += dz1x[r * 32 + i];
       }
       csync();
@@ -535,7 +536,7 @@ core_bwd_pipe_tc(const BwdArgs a, const int P, const int ntiles, int *progress) 
         if (tid == 0) st_release_gpu_bt(my_flag, it + 1);  // release at gpu scope, cumulative over the barrier above
       }
       for (int e = tid; e < nmy * C; e += PNT) {  // dW (1x1 conv) operand stash: off the stage-to-stage path
-        const int r = e / C, j = e - r * C;
+        const int r = fast_div(e, magC), j = e - r * C;
         const size_t o = (cell * B + row0 + lr0 + r) * C + j;
         if (a.dzf) a.dzf[o] = dzf[r * pC + j];
         if (a.pdzf_hi) put_plane(a.pdzf_hi, a.pdzf_lo, o, dzf[r * pC + j]);

@@ -105,6 +105,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
   const int c = (int)cluster.block_rank();
   const int stage = blockIdx.y, nk = gridDim.y, k = a.k_first + stage, p = blockIdx.z;
   const int C = d.C, Ci = d.Ci, Cz = d.Cz, Co = d.Co, H = d.H, GH = d.GH, B = a.B, Tp = a.Tp, Cp = d.Cp, Cip = d.Cip;
+  const unsigned magC = div_magic(C);
   const PlanTC pl = plan_tc(d);
   const int pC = pl.pC, pO = pl.pO;
   float *wsm = (float *)(smb + pl.w);
@@ -287,7 +288,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
       auto fetch_x = [&]() {
 #pragma unroll
         for (int i = 0; i < XI; ++i) {
-          const int e = tid + PNT * i, r = e / C, cc = e - r * C;
+          const int e = tid + PNT * i, r = fast_div(e, magC), cc = e - r * C;
           xv[i] = 0.f;
           if (e < PRH * C && r < nmy) {
             const int b = row0 + lr0 + r;
@@ -307,7 +308,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
       }
 #pragma unroll
       for (int i = 0; i < XI; ++i) {
-        const int e = tid + PNT * i, r = e / C, cc = e - r * C;
+        const int e = tid + PNT * i, r = fast_div(e, magC), cc = e - r * C;
         if (e < PRH * C) {
           float v = 0.f;
           if (r < nmy) {
@@ -361,7 +362,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
       fence_async_smem();
       cluster_arrive_();  // A: z1 complete in both CTAs (the MMA warp joins once its recurrent product is done)
       for (int e = tid; e < nmy * C; e += PNT) {  // y stash of this CTA's rows (fp32 and operand planes) inside the barrier window
-        const int r = e / C, j = e - r * C;
+        const int r = fast_div(e, magC), j = e - r * C;
         const size_t o = (cell * B + row0 + lr0 + r) * C + j;
         const float yv = xs[r * pC + j];
         if (a.st_y) a.st_y[o] = yv;
@@ -483,7 +484,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
         }
       }
       for (int e = tid; e < nmy * C; e += PNT) {  // zf stash of this CTA's rows (fp32 and operand planes) 
-        const int r = e / C, j = e - r * C;
+        const int r = fast_div(e, magC), j = e - r * C;
         const size_t o = (cell * B + row0 + lr0 + r) * C + j;
         const float zv = zrow[r * pC + j];
         if (a.st_zf) a.st_zf[o] = zv;
@@ -548,7 +549,7 @@ core_fwd_pipe_tc(const FwdArgs a, const int P, const int ntiles, int *progress) 
       csync();
       {
         float *dst = last ? a.z_out + (size_t)t * B * C : a.xin + (cell + Tp) * B * C;  // XIN[k+1][t]
-        for (int e = tid; e < nmy * C; e += PNT) { const int r = e / C, j = e - r * C; dst[(size_t)(row0 + lr0 + r) * C + j] = zrow[r * pC + j]; }
+        for (int e = tid; e < nmy * C; e += PNT) { const int r = fast_div(e, magC), j = e - r * C; dst[(size_t)(row0 + lr0 + r) * C + j] = zrow[r * pC + j]; }
       }
       if (!last) {
         csync();
