@@ -33,7 +33,9 @@ namespace tc {
 constexpr int BM = 128;        // tile rows (UMMA M, cta_group::1)
 constexpr int BK = 64;         // bf16 elements per k-block = one 128-byte swizzle span
 constexpr int UK = 16;         // UMMA K for 16-bit operands
-constexpr int kEpiWarps = 8;       // generic epilogue; the fused GRU forward runs kGruEpiWarps (its epilogue is latency bound)
+constexpr int kEpiWarps = 12;      // generic epilogue: three warps per TMEM lane quarter take alternate 16-column passes.  12 instead of 8
+                                   // (round 2): the epilogue-heavy launches (plane outputs, LeakyReLU', column sums on short K) were bound by
+                                   // it - CTA-pair GEMMs of a step 2.13 -> 1.97 ms; 125 registers, no spills; 16 warps would cost a ring stage
 constexpr int kGruEpiWarps = 8;   // (16 epilogue warps were measured slower: 96 registers per thread spill, 2.88 vs 2.37 ms per step)
 constexpr int kThreads = 64 + 32 * kEpiWarps;  // TMA warp + MMA warp + epilogue warps
 __host__ __device__ constexpr int threads_for(int ew) { return 64 + 32 * ew; }
