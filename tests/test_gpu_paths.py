@@ -274,3 +274,30 @@ def test_hybrid_wavefronts_match_ffma_wavefronts_and_oracle(rnn, H, K, B):
         oref = P[k_].grad.double()
         oerr = float((g1[k_].double().cpu().reshape(oref.shape) - oref).norm() / oref.norm().clamp_min(1e-30))
         assert oerr < 5e-3, (k_, oerr)
+
+
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 2e-5), ("bf16", 5e-3)])
+@pytest.mark.parametrize("B", [256, 100])
+def test_input_projection_inside_the_step_gemm_matches_separate_projection(mode, tol, B):
+    """Encoder window steps with the input projection inside the fused step GEMM (LFI_FUSE_GRU_FWD_X: masked window-input planes x
+    W_ih as an extra k-block, step 0 = the input part alone; LFI_ENC_XFUSE=1, the default) against the same steps fetching the rows
+    of a separate per-frame projection GEMM in the epilogue (LFI_ENC_XFUSE=0): z / NLL and every gradient (the backward pass reads
+    the window-input planes the FORWARD pass gathered).  Frame-dropout masks on - the mask scales the A rows of the extra
+    k-block instead of the projected rows.  B=100 leaves a ragged last tile."""
+    hp, m = _model(mode)
+    hy = O.Hyper.from_hparams(hp)
+    m.train()
+    T = 80
+    batch = to_device(kat_batch(hp, B, T, seed=33), DEV)
+    masks = O.make_masks(hy, B, T - hy.start_ts, seed=34)
+    m.injected_masks = {k: (v.to(DEV) if v is not None else None) for k, v in masks.items()}
+    with _env(LFI_ENC_XFUSE="1"):
+        z1, n1, g1 = _fwd_bwd(m, batch)
+    with _env(LFI_ENC_XFUSE="0"):
+        z0, n0, g0 = _fwd_bwd(m, batch)
+    assert relerr(z1, z0) < 5 * tol
+    assert relerr(n1, n0) < (1e-5 if mode == "bf16x3" else 1e-4)
+    for k in g0:
+        ref = g0[k].double()
+        err = float((g1[k].double() - ref).norm() / ref.norm().clamp_min(1e-30))
+        assert err < (2e-3 if mode == "bf16x3" else 0.1), (k, err)
