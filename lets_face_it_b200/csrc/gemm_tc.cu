@@ -636,8 +636,8 @@ gemm_tc_kernel(const Params p, const __grid_constant__ CUtensorMap mapA0, const 
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
-    // Warp w may read TMEM lanes [32*(w%4), +32).  Two warps share a lane quarter and take alternate 16-column
+    // ===================== epilogue (warps 2 .. 2+EW-1) =====================
+    // Warp w may read TMEM lanes [32*(w%4), +32).  EW/4 warps share a lane quarter and take alternate 16-column
     // passes: tcgen05.ld (thread = row) -> shared-memory transpose -> 128-bit global accesses in which four lanes
     // cover 64 contiguous bytes of a row.  Operands of the read-modify-write epilogues are prefetched before the
     // TMEM load so their latency overlaps it.
