@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--sample-seqs", type=int, default=1024, help="concurrent sequences per GPU of the sampling leg")
     ap.add_argument("--sample-frames", type=int, default=750, help="generated frames per sequence (30 s at 25 fps)")
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling (secondary number, SURVEY.md section 8(d) config 3): the GLOBAL batch stays --batch, each GPU takes batch / N")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-batch", type=int, default=256, help="sequences per step of the CPU reference arm (default: the same B=256 step as our arm)")
     ap.add_argument("--no-sample", action="store_true")
@@ -242,6 +244,10 @@ def run_ours(a):
     hy = O.Hyper.from_hparams(hp)
     gemm_mode = {"fp32": cabi.GEMM_FP32, "bf16x3": cabi.GEMM_BF16X3, "bf16": cabi.GEMM_BF16}[a.gemm]
     B, T = a.batch, T_TRAIN
+    if a.strong:
+        if a.batch % world:
+            raise SystemExit("--strong: --batch %d is not divisible by %d GPUs" % (a.batch, world))
+        B = a.batch // world
     Tp = T - hy.start_ts
     model = build_kat_model(hp)          # seeds 1234 / 7: identical replicas on every rank
     model = model.to(dev).train()
@@ -400,7 +406,7 @@ def run_ours(a):
 
     out = {
         "metric": "train frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if a.strong else "weak", "vs_baseline": None,
         "dtype": "f32" if a.gemm != "bf16" else "bf16", "data": "synthetic",
         "config": {"workload": "%s training step (fwd+NLL+bwd+clip20+Adam), B=%d sequences/GPU, T=80 (56 trained "
                                "frames/seq), frame dropout on" % ("final_model.yaml" if a.variant == "final" else
